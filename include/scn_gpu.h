@@ -1,0 +1,180 @@
+/*
+ * scn_gpu.h — C ABI of libscn_gpu.so, the B200 (sm_100a) device-side replacement for the search
+ * hot path of Scintirete's internal/core/algorithm package.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a cgo binding of the
+ * reference's index/distance interfaces would call (see INTEGRATION.md for the Go side). Plain
+ * pointers and sizes only; the caller owns every buffer; the library never keeps a caller pointer
+ * past return. All citations are relative to the reference tree.
+ *
+ *   reference interface                                   replaced / mirrored by
+ *   ----------------------------------------------------  ---------------------------------------
+ *   algorithm.NewHNSW / NewDistanceCalculator              scn_store_create           (hnsw.go:128-145, distance.go:129-140)
+ *   HNSW.Insert / Build (vector storage half)              scn_store_append[_dev]     (hnsw.go:148-187, collection.go:71-149)
+ *   HNSW.Delete (soft delete flag)                         scn_store_mark_deleted     (hnsw.go:260-289)
+ *   HNSW.ImportGraphState / ExportGraphState hand-off      scn_graph_upload           (hnsw.go:703-804, interfaces.go:137-151)
+ *   HNSW.Search + searchLayer + rerank                     scn_search_hnsw[_dev]      (hnsw.go:292-350, 487-557)
+ *   BatchDistance + stable sort (flat / exact scan)        scn_search_flat[_dev]      (distance.go:144-150)
+ *   HNSW.Search rerank step on caller-chosen candidates    scn_rerank                 (hnsw.go:317-347)
+ *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
+ *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
+ *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev
+ *
+ * Status codes are the reference's utils.ErrorCode numbers (internal/utils/errors.go:11-49) so the
+ * Go shim can wrap them with utils.NewError(code, scn_last_error()).
+ *
+ * Threading: search entry points are re-entrant and may be called concurrently from any OS thread
+ * (the reference allows concurrent Search under RLock, hnsw.go:293). Mutators (append, mark_deleted,
+ * graph_upload, clear) require the caller's write lock (hnsw.go:178, 261, 750), exactly as in the
+ * reference. All calls block until outputs are valid, except the *_dev variants, which enqueue on
+ * the given CUDA stream and return.
+ */
+#ifndef SCN_GPU_H_
+#define SCN_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SCN_API __attribute__((visibility("default")))
+#else
+#define SCN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* types.DistanceMetric (pkg/types/types.go:12-19); values cross the ABI unchanged. */
+enum {
+  SCN_METRIC_UNSPECIFIED = 0,
+  SCN_METRIC_L2 = 1,
+  SCN_METRIC_COSINE = 2,
+  SCN_METRIC_INNER_PRODUCT = 3
+};
+
+/* utils.ErrorCode subset (internal/utils/errors.go:11-49). 0 = success. */
+enum {
+  SCN_OK = 0,
+  SCN_ERR_INTERNAL = 1000,           /* CUDA / driver failure */
+  SCN_ERR_RESOURCE = 1003,           /* out of device memory */
+  SCN_ERR_VECTOR_NOT_FOUND = 3004,
+  SCN_ERR_DIMENSION_MISMATCH = 3005,
+  SCN_ERR_INVALID_PARAMETERS = 3007,
+  SCN_ERR_INDEX_BUILD_FAILED = 5000,
+  SCN_ERR_SEARCH_FAILED = 5001,
+  SCN_ERR_INSERT_FAILED = 5002
+};
+
+typedef struct scn_store scn_store;
+
+typedef struct scn_stats {
+  uint64_t rows;          /* rows appended (including soft-deleted) */
+  uint64_t live_rows;     /* rows not soft-deleted == HNSW.Size() */
+  uint64_t capacity_rows;
+  uint64_t device_bytes;  /* bytes of HBM held by the store */
+  uint32_t dim;
+  int32_t metric;
+  int32_t device;
+  int32_t has_graph;
+  int32_t max_layer;      /* HNSW maxLayer, -1 if no graph */
+  int32_t m;              /* HNSW M of the uploaded graph */
+  uint64_t entry_id;      /* HNSW entrypoint, 0 = none */
+  uint64_t graph_edges;
+} scn_stats;
+
+/* Thread-local message for the last non-zero status returned on this thread. */
+SCN_API const char* scn_last_error(void);
+
+/* Number of kernels launched by this library in this process so far (all threads). */
+SCN_API uint64_t scn_launch_count(void);
+
+/* ---- device vector store ------------------------------------------------------------------ */
+
+/* metric must be 1, 2 or 3 (else SCN_ERR_INVALID_PARAMETERS, like NewDistanceCalculator). */
+SCN_API int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store** out);
+SCN_API int32_t scn_store_destroy(scn_store* s);
+SCN_API int32_t scn_store_reserve(scn_store* s, uint64_t rows);
+SCN_API int32_t scn_store_clear(scn_store* s);
+
+/* Appends n row-major fp32 vectors (host memory). ids == NULL assigns id = row + 1, the
+ * reference's auto-increment (collection.go:57,115-116). id 0 and duplicate ids are rejected
+ * (SCN_ERR_INVALID_PARAMETERS; hnsw.go:192-194, 210). Norms and the bf16 mirror are computed on
+ * the device. */
+SCN_API int32_t scn_store_append(scn_store* s, const float* vecs, const uint64_t* ids, uint64_t n);
+/* Same, with vectors already in device memory (ids, if given, in host memory). */
+SCN_API int32_t scn_store_append_dev(scn_store* s, const float* d_vecs, const uint64_t* ids, uint64_t n);
+
+/* Soft delete (HNSW.Delete). Unknown id -> SCN_ERR_VECTOR_NOT_FOUND; already deleted is a no-op. */
+SCN_API int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n);
+
+SCN_API int32_t scn_store_stats(scn_store* s, scn_stats* out);
+
+/* Copies row vectors back to the host by id (HNSW.Get); out is [n][dim]. */
+SCN_API int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, float* out);
+
+/* ---- HNSW graph hand-off -------------------------------------------------------------------
+ * Flattened core.HNSWGraphState: for node i (any order), node_ids[i], list_counts[i] =
+ * len(Connections) (level + 1); then for each of its lists, in layer order, edge_counts[...]
+ * neighbour ids concatenated in `edges`. Every node id and neighbour id must already be in the
+ * store. m is HNSWParams.M (layer-0 lists hold at most 2*m, upper lists m; longer lists are
+ * rejected). entry_id / max_layer are HNSW.entrypoint / maxLayer verbatim. Replaces any previous
+ * graph. */
+SCN_API int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t entry_id, uint64_t n_nodes,
+                         const uint64_t* node_ids, const int32_t* list_counts, const uint32_t* edge_counts,
+                         const uint64_t* edges);
+
+/* ---- search (host buffers; blocking) -------------------------------------------------------
+ * q is [nq][dim] fp32. Outputs are [nq][k]: ids (0 = none) and distances (+Inf = none), sorted by
+ * (distance, insertion row) ascending; out_counts[nq] (may be NULL) = number of valid results. */
+
+/* Exact scan over all live rows. Identical to BatchDistance + stable sort + truncate. */
+SCN_API int32_t scn_search_flat(scn_store* s, const float* q, uint64_t nq, uint32_t k, uint64_t* out_ids,
+                        float* out_dist, uint32_t* out_counts);
+
+/* HNSW.Search for nq queries. ef <= 0 is invalid here: the Go shim resolves
+ * SearchParams.EfSearch / HNSWParams.EfSearch before the call (hnsw.go:300-303). Result count per
+ * query is min(k, ef, reachable), as in the reference. */
+SCN_API int32_t scn_search_hnsw(scn_store* s, const float* q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                        float* out_dist, uint32_t* out_counts);
+
+/* Exact distances for caller-chosen candidates, then top-k: cand_ids is [nq][ncand] (0 = empty
+ * slot; unknown or deleted ids are skipped). */
+SCN_API int32_t scn_rerank(scn_store* s, const float* q, uint64_t nq, const uint64_t* cand_ids, uint32_t ncand, uint32_t k,
+                   uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
+
+/* out[i*nx + j] = Distance(q_i, x_j) with the reference's exact fp32 arithmetic. */
+SCN_API int32_t scn_distance_batch(int32_t device, int32_t metric, const float* q, uint64_t nq, const float* x, uint64_t nx,
+                           uint32_t dim, float* out);
+
+/* ---- search (device buffers; asynchronous on `stream`, a cudaStream_t) ---------------------- */
+SCN_API int32_t scn_search_flat_dev(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_out_ids,
+                            float* d_out_dist, uint32_t* d_out_counts, void* stream);
+SCN_API int32_t scn_search_hnsw_dev(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                            float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/* Row-sharded search, shard-local half: like scn_search_flat_dev but additionally writes
+ * d_out_keys[nq][k], the 64-bit merge keys (order-preserving distance bits << 32 | global row,
+ * global row = row_base + local row; ~0 = none), so shards can be merged exactly. */
+SCN_API int32_t scn_search_flat_shard_dev(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
+                                  uint64_t* d_out_keys, uint64_t* d_out_ids, void* stream);
+/* Merge of G per-shard results laid out [G][nq][k] (e.g. the output of an NCCL all-gather) into
+ * the global top-k with the flat scan's (distance, row) order. */
+SCN_API int32_t scn_merge_topk_dev(int32_t device, const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq,
+                           uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/* ---- tuning / introspection ---------------------------------------------------------------- */
+/* Options: "flat_path" 0 = auto, 1 = exact CUDA-core scan only, 2 = tensor-core filter + exact
+ * rerank; "tensor_min_batch" (auto crossover); "overfetch" (candidates kept per query and column
+ * block by the tensor filter); "profile" 1 = record per-kernel CUDA-event timings. */
+SCN_API int32_t scn_set_option(scn_store* s, const char* name, int64_t value);
+/* Per-kernel timings of the last profiled search on this store: names[i] -> ms[i]; returns count. */
+SCN_API int32_t scn_last_timings(scn_store* s, const char** names, float* ms, int32_t max_entries);
+/* Counters of the last flat search: [0] queries served by the tensor path, [1] queries whose
+ * certificate failed and were re-scanned exactly, [2] candidates reranked. */
+SCN_API int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCN_GPU_H_ */

@@ -1,0 +1,80 @@
+"""ctypes binding of libscn_gpu.so — the same C ABI the Go cgo shim binds (include/scn_gpu.h).
+
+There is no CPU fallback: if the library is missing or no B200 is present, calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscn_gpu.so")
+
+f32p = C.POINTER(C.c_float)
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+
+
+class Stats(C.Structure):
+    _fields_ = [("rows", C.c_uint64), ("live_rows", C.c_uint64), ("capacity_rows", C.c_uint64),
+                ("device_bytes", C.c_uint64), ("dim", C.c_uint32), ("metric", C.c_int32), ("device", C.c_int32),
+                ("has_graph", C.c_int32), ("max_layer", C.c_int32), ("m", C.c_int32), ("entry_id", C.c_uint64),
+                ("graph_edges", C.c_uint64)]
+
+
+# every symbol include/scn_gpu.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "scn_last_error": (C.c_char_p, []),
+    "scn_launch_count": (C.c_uint64, []),
+    "scn_store_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "scn_store_destroy": (C.c_int32, [C.c_void_p]),
+    "scn_store_reserve": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "scn_store_clear": (C.c_int32, [C.c_void_p]),
+    "scn_store_append": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_store_append_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_store_mark_deleted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_store_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
+    "scn_store_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "scn_graph_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "scn_search_flat": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_search_hnsw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "scn_rerank": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
+    "scn_distance_batch": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
+                                        C.c_void_p]),
+    "scn_search_flat_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "scn_search_hnsw_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_search_flat_shard_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]),
+    "scn_merge_topk_dev": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "scn_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), f32p, C.c_int32]),
+    "scn_last_counters": (C.c_int32, [C.c_void_p, u64p, C.c_int32]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m scintirete_b200.build` (nvcc, sm_100a). "
+                "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the header diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().scn_last_error() or b"").decode("utf-8", "replace")

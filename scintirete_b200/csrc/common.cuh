@@ -1,0 +1,153 @@
+// common.cuh — shared host/device helpers for libscn_gpu (B200 / sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/scn_gpu.h"
+
+namespace scn {
+
+// ---- error plumbing (status codes = utils.ErrorCode, internal/utils/errors.go:11-49) --------
+int32_t fail(int32_t code, const char* fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(uint64_t n = 1);
+
+#define SCN_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) return scn::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define SCN_TRY(expr)            \
+  do {                           \
+    int32_t rc__ = (expr);       \
+    if (rc__ != SCN_OK) return rc__; \
+  } while (0)
+
+// after a kernel launch
+#define SCN_LAUNCHED()                                                         \
+  do {                                                                         \
+    scn::count_launch();                                                       \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) return scn::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// ---- order-preserving distance keys ---------------------------------------------------------
+// key = ord(dist) << 32 | row. Ascending u64 order == (distance ascending, row ascending), the
+// flat oracle's stable order. -0.0 is folded into +0.0 (they compare equal in the reference's
+// float comparisons); any NaN sorts after +Inf (a NaN is never "<" anything in the reference).
+__host__ __device__ __forceinline__ uint32_t f32_ord(float d) {
+  if (d != d) return 0xFFFFFFFFu;
+  d = d + 0.0f;
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(d);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = d;
+  uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__host__ __device__ __forceinline__ float ord_f32(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c;
+  c.u = u;
+  return c.f;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint64_t make_key(float d, uint32_t row) {
+  return ((uint64_t)f32_ord(d) << 32) | row;
+}
+
+constexpr uint64_t KEY_NONE = ~0ull;
+constexpr uint32_t ROW_NONE = 0xFFFFFFFFu;
+
+// ---- the reference's arithmetic, bit for bit -------------------------------------------------
+// Go on amd64 rounds every float32 multiply and add separately (no FMA) and accumulates in
+// source order (distance.go:26-30, 58-63, 109-112). __fmul_rn/__fadd_rn/__fsub_rn are never
+// contracted by nvcc, so these reproduce the reference's bits exactly.
+enum : int { M_L2 = SCN_METRIC_L2, M_COS = SCN_METRIC_COSINE, M_IP = SCN_METRIC_INNER_PRODUCT };
+
+template <int METRIC>
+__device__ __forceinline__ float acc_step(float acc, float q, float x) {
+  if (METRIC == M_L2) {
+    float diff = __fsub_rn(q, x);
+    return __fadd_rn(acc, __fmul_rn(diff, diff));
+  } else {
+    return __fadd_rn(acc, __fmul_rn(q, x));
+  }
+}
+
+// acc = the sequential sum; qnorm / xnorm = sqrt of the sequential sums of squares (cosine only).
+template <int METRIC>
+__device__ __forceinline__ float finish_distance(float acc, float qnorm, float xnorm) {
+  if (METRIC == M_L2) return __fsqrt_rn(acc);                  // distance.go:31
+  if (METRIC == M_IP) return -acc;                             // distance.go:115
+  if (qnorm == 0.0f || xnorm == 0.0f) return 1.0f;             // distance.go:68-70
+  float cs = __fdiv_rn(acc, __fmul_rn(qnorm, xnorm));          // distance.go:72
+  if (cs > 1.0f) cs = 1.0f;
+  else if (cs < -1.0f) cs = -1.0f;                              // distance.go:74-78
+  return __fsub_rn(1.0f, cs);                                  // distance.go:81
+}
+
+// One thread, one (query,row) pair, reference order. q and x must be 16-byte aligned with
+// `pitch4` float4s readable (zero padded past dim: adding +0.0 terms never changes the sum).
+template <int METRIC>
+__device__ __forceinline__ float exact_acc_thread(const float* __restrict__ q, const float* __restrict__ x,
+                                                  uint32_t pitch4) {
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float acc = 0.0f;
+#pragma unroll 4
+  for (uint32_t i = 0; i < pitch4; ++i) {
+    float4 a = q4[i];
+    float4 b = __ldg(x4 + i);
+    acc = acc_step<METRIC>(acc, a.x, b.x);
+    acc = acc_step<METRIC>(acc, a.y, b.y);
+    acc = acc_step<METRIC>(acc, a.z, b.z);
+    acc = acc_step<METRIC>(acc, a.w, b.w);
+  }
+  return acc;
+}
+
+// sequential sum of squares -> sqrt, i.e. VectorMagnitude (distance.go:175-181) and the normA /
+// normB terms of CosineDistance (distance.go:58-66)
+__device__ __forceinline__ float exact_norm_thread(const float* __restrict__ v, uint32_t n) {
+  float s = 0.0f;
+  for (uint32_t i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(v[i], v[i]));
+  return __fsqrt_rn(s);
+}
+
+__device__ __forceinline__ bool bit_test(const uint32_t* __restrict__ bits, uint32_t i) {
+  return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
+}
+
+// ---- cp.async helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+inline uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace scn

@@ -1,0 +1,530 @@
+// flat_exact.cu — exact (bit-faithful) flat scan, exact rerank, batched distances, top-k merges.
+//
+// K1e  flat_exact_scan_kernel : HBM-streaming scan of the fp32 rows. Each thread owns one row of
+//      a 256-row tile and accumulates, in the reference's sequential order and rounding
+//      (distance.go:26-30, 58-63, 109-112), the distance to up to QB queries at once. Tiles are
+//      staged through shared memory with 16-byte cp.async (coalesced 128-byte row segments, three
+//      stages in flight), read back conflict-free as float4 (row pitch 36 floats).
+//      Roofline: HBM. Algorithmic bytes per pass = N*pitch*4 (+ N*4 norms for cosine).
+// K4   block top-k: per-query sorted key lists in shared memory, threshold-gated queues.
+// K3   rerank_kernel : exact distances for gathered candidate rows + block bitonic top-k.
+// K7   merge_topk_kernel : per-query merge of G sorted shard lists.
+#include "store.h"
+
+namespace scn {
+
+constexpr int SCAN_THREADS = 256;  // rows per tile
+constexpr int SCAN_KC = 32;        // floats of each row per stage
+constexpr int SCAN_PITCH = 36;     // smem row pitch in floats (16B aligned, conflict-free LDS.128)
+constexpr int SCAN_STAGES = 3;
+
+// ---- warp-cooperative sorted-list insertion ---------------------------------------------------
+// list[0..k) ascending, KEY_NONE padded. Inserts x if x < list[k-1]. All 32 lanes participate.
+__device__ __forceinline__ void warp_list_insert(uint64_t* list, uint32_t k, uint64_t x, int lane) {
+  if (x >= list[k - 1]) return;
+  // position = number of entries < x
+  uint32_t pos = 0;
+  for (uint32_t base = 0; base < k; base += 32) {
+    uint32_t i = base + lane;
+    bool lt = (i < k) && (list[i] < x);
+    pos += __popc(__ballot_sync(0xffffffffu, lt));
+  }
+  // shift [pos, k-2] right by one, highest chunk first
+  for (int base = (int)((k - 1) / 32) * 32; base >= 0; base -= 32) {
+    uint32_t i = base + lane;  // destination index
+    uint64_t v = 0;
+    bool mv = (i < k) && (i > pos);
+    if (mv) v = list[i - 1];
+    __syncwarp();
+    if (mv) list[i] = v;
+    __syncwarp();
+  }
+  if (lane == 0) list[pos] = x;
+  __syncwarp();
+}
+
+// block-wide bitonic sort of n (power of two) u64 keys in shared memory
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* a, uint32_t n) {
+  for (uint32_t size = 2; size <= n; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        uint32_t lo = 2 * t - (t & (stride - 1));
+        uint32_t hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        uint64_t x = a[lo], y = a[hi];
+        if ((x > y) == up) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- K1e ------------------------------------------------------------------------------------
+struct ScanParams {
+  const float* vec;
+  const float* norm;
+  const uint32_t* deleted;
+  uint32_t pitch;     // floats
+  uint32_t n_rows;
+  uint32_t dim_pad;   // dim rounded up to SCAN_KC
+  const float* q;     // [.][pitch_q] device queries
+  uint32_t q_pitch;   // floats between queries in q
+  uint32_t q_dim;     // valid floats per query
+  const uint32_t* qlist;   // optional: indices into q
+  const uint32_t* nq_dev;  // optional: device-resident number of queries (<= nq)
+  uint32_t nq;
+  uint32_t k;
+  uint32_t row_base;  // added to the row field of the emitted keys
+  uint64_t* partial;  // [gridDim.x][nq][k]
+};
+
+template <int METRIC, int QB>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t k = p.k;
+  float* s_q = reinterpret_cast<float*>(smem_raw);                    // [QB][dim_pad]
+  float* s_tile = s_q + (size_t)QB * p.dim_pad;                       // [STAGES][256][PITCH]
+  uint64_t* s_queue = reinterpret_cast<uint64_t*>(s_tile + (size_t)SCAN_STAGES * SCAN_THREADS * SCAN_PITCH);  // [QB][256]
+  uint64_t* s_list = s_queue + (size_t)QB * SCAN_THREADS;             // [QB][k]
+  __shared__ uint64_t s_tau[QB];
+  __shared__ uint32_t s_qcount[QB];
+  __shared__ float s_qnorm[QB];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t nq_total = p.nq_dev ? min(*p.nq_dev, p.nq) : p.nq;
+  const uint32_t n_tiles = (p.n_rows + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t n_chunks = p.dim_pad / SCAN_KC;
+
+  for (uint32_t q0 = 0; q0 < nq_total; q0 += QB) {
+    const uint32_t nq_here = min((uint32_t)QB, nq_total - q0);
+    __syncthreads();
+    // queries -> smem (zero padded), lists -> KEY_NONE
+    for (uint32_t i = tid; i < QB * p.dim_pad; i += SCAN_THREADS) {
+      uint32_t qi = i / p.dim_pad, e = i - qi * p.dim_pad;
+      float v = 0.0f;
+      if (qi < nq_here && e < p.q_dim) {
+        uint32_t src = p.qlist ? p.qlist[q0 + qi] : (q0 + qi);
+        v = p.q[(size_t)src * p.q_pitch + e];
+      }
+      s_q[i] = v;
+    }
+    for (uint32_t i = tid; i < QB * k; i += SCAN_THREADS) s_list[i] = KEY_NONE;
+    if (tid < QB) {
+      s_tau[tid] = KEY_NONE;
+      s_qcount[tid] = 0;
+    }
+    __syncthreads();
+    if (METRIC == M_COS && tid < QB) s_qnorm[tid] = exact_norm_thread(s_q + (size_t)tid * p.dim_pad, p.q_dim);
+    __syncthreads();
+
+    // flattened (tile, chunk) pipeline over this block's tiles
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total = my_tiles * n_chunks;
+    auto issue = [&](uint32_t it) {
+      if (it < total) {
+        uint32_t tile = blockIdx.x + (it / n_chunks) * gridDim.x;
+        uint32_t chunk = it % n_chunks;
+        float* dst = s_tile + (size_t)(it % SCAN_STAGES) * SCAN_THREADS * SCAN_PITCH;
+        // 256 rows x 8 segments of 16 B; consecutive threads take consecutive segments of a row
+#pragma unroll
+        for (int j = 0; j < (SCAN_THREADS * 8) / SCAN_THREADS; ++j) {
+          uint32_t idx = j * SCAN_THREADS + tid;
+          uint32_t r = idx >> 3, seg = idx & 7;
+          uint32_t row = tile * SCAN_THREADS + r;
+          uint32_t col = chunk * SCAN_KC + seg * 4;
+          bool valid = (row < p.n_rows) && (col < p.pitch);
+          const float* src = p.vec + (size_t)(valid ? row : 0) * p.pitch + (valid ? col : 0);
+          cp_async16(dst + r * SCAN_PITCH + seg * 4, src, valid);
+        }
+      }
+      cp_async_commit();
+    };
+    for (int s = 0; s < SCAN_STAGES - 1; ++s) issue(s);
+
+    float acc[QB];
+    for (uint32_t it = 0; it < total; ++it) {
+      const uint32_t chunk = it % n_chunks;
+      if (chunk == 0) {
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.0f;
+      }
+      cp_async_wait<SCAN_STAGES - 2>();
+      __syncthreads();                 // stage `it` landed for everyone; stage it-1 is free
+      issue(it + SCAN_STAGES - 1);
+      const float4* x4 = reinterpret_cast<const float4*>(s_tile + (size_t)(it % SCAN_STAGES) * SCAN_THREADS * SCAN_PITCH +
+                                                          tid * SCAN_PITCH);
+#pragma unroll
+      for (int j = 0; j < SCAN_KC / 4; ++j) {
+        float4 x = x4[j];
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) {
+          float4 qv = *reinterpret_cast<const float4*>(s_q + (size_t)qi * p.dim_pad + chunk * SCAN_KC + j * 4);
+          acc[qi] = acc_step<METRIC>(acc[qi], qv.x, x.x);
+          acc[qi] = acc_step<METRIC>(acc[qi], qv.y, x.y);
+          acc[qi] = acc_step<METRIC>(acc[qi], qv.z, x.z);
+          acc[qi] = acc_step<METRIC>(acc[qi], qv.w, x.w);
+        }
+      }
+      if (chunk == n_chunks - 1) {
+        // tile finished: gate against the block threshold, queue, merge
+        uint32_t tile = blockIdx.x + (it / n_chunks) * gridDim.x;
+        uint32_t row = tile * SCAN_THREADS + tid;
+        bool live = (row < p.n_rows) && !bit_test(p.deleted, row);
+        float xn = (METRIC == M_COS && live) ? __ldg(p.norm + row) : 0.0f;
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) {
+          if (qi < (int)nq_here && live) {
+            float d = finish_distance<METRIC>(acc[qi], s_qnorm[qi], xn);
+            uint64_t key = make_key(d, row + p.row_base);
+            if (key < s_tau[qi]) {
+              uint32_t slot = atomicAdd(&s_qcount[qi], 1u);
+              s_queue[(size_t)qi * SCAN_THREADS + slot] = key;
+            }
+          }
+        }
+        __syncthreads();
+        for (uint32_t qi = warp; qi < nq_here; qi += SCAN_THREADS / 32) {
+          uint32_t cnt = s_qcount[qi];
+          if (cnt) {
+            uint64_t* list = s_list + (size_t)qi * k;
+            for (uint32_t c = 0; c < cnt; ++c) warp_list_insert(list, k, s_queue[(size_t)qi * SCAN_THREADS + c], lane);
+            if (lane == 0) {
+              s_tau[qi] = list[k - 1];
+              s_qcount[qi] = 0;
+            }
+          }
+        }
+        // the next __syncthreads (top of the loop) orders these writes before the next gate
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    for (uint32_t i = tid; i < nq_here * k; i += SCAN_THREADS) {
+      uint32_t qi = i / k, j = i - qi * k;
+      p.partial[((size_t)blockIdx.x * p.nq + (q0 + qi)) * k + j] = s_list[(size_t)qi * k + j];
+    }
+  }
+}
+
+// ---- partial-list merge: one block per query, P sorted lists of k -> k -------------------------
+// buf holds `cap` keys (power of two >= max(2*kp, 2048)); each round appends cap-kp fresh keys
+// behind the current best kp, sorts, and keeps the first kp.
+__global__ void __launch_bounds__(256) merge_partials_kernel(const uint64_t* __restrict__ partial, uint32_t n_parts,
+                                                             uint32_t nq_stride, const uint32_t* __restrict__ qlist,
+                                                             const uint32_t* __restrict__ nq_dev, uint32_t k, uint32_t kp,
+                                                             uint32_t cap, uint64_t* __restrict__ out_keys) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // [cap]
+  uint32_t q = blockIdx.x;
+  if (nq_dev && q >= *nq_dev) return;
+  for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) buf[i] = KEY_NONE;
+  const uint64_t total = (uint64_t)n_parts * k;
+  const uint32_t fresh = cap - kp;
+  for (uint64_t base = 0; base < total; base += fresh) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < fresh; i += blockDim.x) {
+      uint64_t g = base + i;
+      uint64_t v = KEY_NONE;
+      if (g < total) {
+        uint32_t part = (uint32_t)(g / k), j = (uint32_t)(g % k);
+        v = partial[((size_t)part * nq_stride + q) * k + j];
+      }
+      buf[kp + i] = v;
+    }
+    block_bitonic_sort(buf, cap);  // best kp stay in buf[0..kp)
+  }
+  __syncthreads();
+  uint32_t dst = qlist ? qlist[q] : q;
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out_keys[(size_t)dst * k + i] = buf[i];
+}
+
+static size_t scan_smem_bytes(int qb, uint32_t dim_pad, uint32_t k) {
+  return (size_t)qb * dim_pad * 4 + (size_t)SCAN_STAGES * SCAN_THREADS * SCAN_PITCH * 4 + (size_t)qb * SCAN_THREADS * 8 +
+         (size_t)qb * k * 8;
+}
+
+template <int METRIC, int QB>
+static int32_t launch_scan(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+  SCN_CUDA(cudaFuncSetAttribute(flat_exact_scan_kernel<METRIC, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  flat_exact_scan_kernel<METRIC, QB><<<grid, SCAN_THREADS, smem, stream>>>(p);
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+template <int METRIC>
+static int32_t launch_scan_qb(int qb, const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+  switch (qb) {
+    case 1: return launch_scan<METRIC, 1>(p, grid, smem, stream);
+    case 2: return launch_scan<METRIC, 2>(p, grid, smem, stream);
+    case 4: return launch_scan<METRIC, 4>(p, grid, smem, stream);
+    default: return launch_scan<METRIC, 8>(p, grid, smem, stream);
+  }
+}
+
+// Exact scan of the whole shard for nq queries (or for the device-side list qlist[0..*nq_dev)).
+// Writes sorted keys [nq][k] (ord(dist)<<32 | row_base+row), KEY_NONE padded.
+int32_t flat_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlist, const uint32_t* d_nq_dev,
+                          uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream,
+                          Profiler* prof) {
+  if (nq == 0) return SCN_OK;
+  if (s->rows == 0) {
+    SCN_CUDA(cudaMemsetAsync(d_out_keys, 0xFF, nq * k * sizeof(uint64_t), stream));
+    return SCN_OK;
+  }
+  int sms = 0;
+  SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  const uint32_t dim_pad = round_up(s->dim, SCAN_KC);
+  // queries per pass: as many as shared memory allows, at most 8
+  int qb = nq >= 8 ? 8 : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
+  while (qb > 1 && scan_smem_bytes(qb, dim_pad, k) > 200 * 1024) qb >>= 1;
+  size_t smem = scan_smem_bytes(qb, dim_pad, k);
+  if (smem > 220 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "k=%u / dim=%u exceed the exact scan's shared memory", k, s->dim);
+  const uint32_t n_tiles = (uint32_t)((s->rows + SCAN_THREADS - 1) / SCAN_THREADS);
+  int grid = (int)std::min<uint32_t>((uint32_t)sms, n_tiles);
+  Scratch scratch(stream);
+  uint64_t* d_partial = nullptr;
+  SCN_TRY(scratch.alloc(&d_partial, (size_t)grid * nq * k));
+  ScanParams p;
+  p.vec = s->d_vec;
+  p.norm = s->d_norm;
+  p.deleted = s->d_deleted;
+  p.pitch = s->pitch;
+  p.n_rows = (uint32_t)s->rows;
+  p.dim_pad = dim_pad;
+  p.q = d_q;
+  p.q_pitch = s->dim;
+  p.q_dim = s->dim;
+  p.qlist = d_qlist;
+  p.nq_dev = d_nq_dev;
+  p.nq = (uint32_t)nq;
+  p.k = k;
+  p.row_base = (uint32_t)row_base;
+  p.partial = d_partial;
+  if (prof) prof->begin("flat_exact_scan");
+  int32_t rc;
+  switch (s->metric) {
+    case M_L2: rc = launch_scan_qb<M_L2>(qb, p, grid, smem, stream); break;
+    case M_COS: rc = launch_scan_qb<M_COS>(qb, p, grid, smem, stream); break;
+    default: rc = launch_scan_qb<M_IP>(qb, p, grid, smem, stream); break;
+  }
+  if (prof) prof->end();
+  SCN_TRY(rc);
+  const uint32_t kp = std::max(32u, next_pow2(k));
+  if (prof) prof->begin("merge_partials");
+  const uint32_t cap = std::max(2 * kp, 2048u);
+  merge_partials_kernel<<<(unsigned)nq, 256, cap * sizeof(uint64_t), stream>>>(d_partial, (uint32_t)grid, (uint32_t)nq,
+                                                                              d_qlist, d_nq_dev, k, kp, cap, d_out_keys);
+  SCN_LAUNCHED();
+  if (prof) prof->end();
+  return SCN_OK;
+}
+
+// ---- keys -> (ids, distances, counts) ---------------------------------------------------------
+__global__ void keys_to_results_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t k, uint32_t row_base,
+                                       const uint64_t* __restrict__ ids, uint64_t* __restrict__ out_ids,
+                                       float* __restrict__ out_dist, uint32_t* __restrict__ out_counts) {
+  uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  uint32_t cnt = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    uint64_t key = keys[q * k + j];
+    if (key == KEY_NONE) {
+      if (out_ids) out_ids[q * k + j] = 0;
+      if (out_dist) out_dist[q * k + j] = __int_as_float(0x7f800000);
+    } else {
+      if (out_ids) out_ids[q * k + j] = ids[(uint32_t)key - row_base];
+      if (out_dist) out_dist[q * k + j] = ord_f32((uint32_t)(key >> 32));
+      ++cnt;
+    }
+  }
+  if (out_counts) out_counts[q] = cnt;
+}
+
+int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64_t row_base, uint64_t* d_out_ids,
+                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream) {
+  if (n == 0) return SCN_OK;
+  keys_to_results_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_keys, n, k, (uint32_t)row_base, s->d_ids,
+                                                                         d_out_ids, d_out_dist, d_out_counts);
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+// ---- K3: exact rerank of gathered candidate rows ------------------------------------------------
+// One block per query. Each thread computes, in reference order, the distance of one candidate
+// row (ROW_NONE / deleted rows are skipped); the block then sorts the keys and emits the top k.
+template <int METRIC>
+__global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ vec, const float* __restrict__ norm,
+                                                     const uint32_t* __restrict__ deleted, uint32_t pitch, uint32_t dim,
+                                                     uint32_t n_rows, const float* __restrict__ q,
+                                                     const uint32_t* __restrict__ cand, uint32_t ncand, uint32_t ncand_pad,
+                                                     uint32_t k, uint32_t row_base, uint64_t* __restrict__ out_keys) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_q = reinterpret_cast<float*>(smem_raw);                    // [pitch]
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q + pitch);        // [ncand_pad]
+  __shared__ float s_qnorm;
+  const uint32_t qi = blockIdx.x;
+  for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) s_q[i] = (i < dim) ? q[(size_t)qi * dim + i] : 0.0f;
+  __syncthreads();
+  if (METRIC == M_COS && threadIdx.x == 0) s_qnorm = exact_norm_thread(s_q, dim);
+  __syncthreads();
+  for (uint32_t c = threadIdx.x; c < ncand_pad; c += blockDim.x) {
+    uint64_t key = KEY_NONE;
+    if (c < ncand) {
+      uint32_t row = cand[(size_t)qi * ncand + c];
+      if (row < n_rows && !bit_test(deleted, row)) {
+        float acc = exact_acc_thread<METRIC>(s_q, vec + (size_t)row * pitch, pitch / 4);
+        float d = finish_distance<METRIC>(acc, METRIC == M_COS ? s_qnorm : 0.0f, METRIC == M_COS ? __ldg(norm + row) : 0.0f);
+        key = make_key(d, row + row_base);
+      }
+    }
+    s_keys[c] = key;
+  }
+  block_bitonic_sort(s_keys, ncand_pad);
+  // drop duplicate rows (a candidate list may name a row twice): keys are identical -> adjacent
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
+    // position i of the de-duplicated sequence; lists are short, a serial prefix is fine
+    out_keys[(size_t)qi * k + i] = KEY_NONE;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t w = 0;
+    uint64_t prev = KEY_NONE;
+    for (uint32_t i = 0; i < ncand_pad && w < k; ++i) {
+      uint64_t v = s_keys[i];
+      if (v == KEY_NONE) break;
+      if (v != prev) out_keys[(size_t)qi * k + w++] = v;
+      prev = v;
+    }
+  }
+}
+
+int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand, uint32_t k,
+                    uint64_t* d_out_keys, cudaStream_t stream) {
+  if (nq == 0) return SCN_OK;
+  uint32_t ncand_pad = std::max(32u, next_pow2(ncand));
+  size_t smem = (size_t)s->pitch * 4 + (size_t)ncand_pad * 8;
+  if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many rerank candidates (%u)", ncand);
+#define RR(MT)                                                                                                    \
+  do {                                                                                                            \
+    SCN_CUDA(cudaFuncSetAttribute(rerank_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    rerank_kernel<MT><<<(unsigned)nq, 128, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,   \
+                                                           (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k, 0, \
+                                                           d_out_keys);                                           \
+  } while (0)
+  switch (s->metric) {
+    case M_L2: RR(M_L2); break;
+    case M_COS: RR(M_COS); break;
+    default: RR(M_IP); break;
+  }
+#undef RR
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+// ---- scn_distance_batch: the scalar DistanceCalculator, one thread per (query, target) ---------
+template <int METRIC>
+__global__ void distance_batch_kernel(const float* __restrict__ q, uint64_t nq, const float* __restrict__ x, uint64_t nx,
+                                      uint32_t dim, float* __restrict__ out) {
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nq * nx) return;
+  const float* a = q + (idx / nx) * dim;
+  const float* b = x + (idx % nx) * dim;
+  float acc = 0.0f, na = 0.0f, nb = 0.0f;
+  for (uint32_t i = 0; i < dim; ++i) {
+    acc = acc_step<METRIC>(acc, a[i], b[i]);
+    if (METRIC == M_COS) {  // distance.go:58-63: three accumulators in one loop
+      na = __fadd_rn(na, __fmul_rn(a[i], a[i]));
+      nb = __fadd_rn(nb, __fmul_rn(b[i], b[i]));
+    }
+  }
+  if (METRIC == M_COS) {
+    na = __fsqrt_rn(na);
+    nb = __fsqrt_rn(nb);
+  }
+  out[idx] = finish_distance<METRIC>(acc, na, nb);
+}
+
+int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const float* d_x, uint64_t nx, uint32_t dim,
+                       float* d_out, cudaStream_t stream) {
+  uint64_t total = nq * nx;
+  if (total == 0) return SCN_OK;
+  unsigned grid = (unsigned)((total + 127) / 128);
+  switch (metric) {
+    case M_L2: distance_batch_kernel<M_L2><<<grid, 128, 0, stream>>>(d_q, nq, d_x, nx, dim, d_out); break;
+    case M_COS: distance_batch_kernel<M_COS><<<grid, 128, 0, stream>>>(d_q, nq, d_x, nx, dim, d_out); break;
+    default: distance_batch_kernel<M_IP><<<grid, 128, 0, stream>>>(d_q, nq, d_x, nx, dim, d_out); break;
+  }
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+// ---- K7: merge of G per-shard lists [G][nq][k] ---------------------------------------------------
+// One warp per query. Keys carry the global row, so ascending key order is exactly the flat
+// oracle's (distance, row) order over the whole database. ids ride along.
+__global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ids,
+                                                         uint32_t n_shards, uint64_t nq, uint32_t k,
+                                                         uint64_t* __restrict__ out_ids, float* __restrict__ out_dist,
+                                                         uint32_t* __restrict__ out_counts) {
+  uint64_t q = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  // each lane owns shards lane, lane+32, ...; heads advance as winners are emitted
+  uint32_t head[8];  // supports up to 256 shards
+#pragma unroll
+  for (int i = 0; i < 8; ++i) head[i] = 0;
+  uint32_t cnt = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    uint64_t best = KEY_NONE;
+    uint32_t best_src = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t sh = lane + 32 * i;
+      if (sh < n_shards && head[i] < k) {
+        uint64_t v = keys[((size_t)sh * nq + q) * k + head[i]];
+        if (v < best) {
+          best = v;
+          best_src = sh;
+        }
+      }
+    }
+    uint64_t wbest = best;
+    for (int o = 16; o > 0; o >>= 1) {
+      uint64_t other = __shfl_xor_sync(0xffffffffu, wbest, o);
+      wbest = other < wbest ? other : wbest;
+    }
+    if (wbest == KEY_NONE) {
+      if (lane == 0) {
+        out_ids[q * k + j] = 0;
+        out_dist[q * k + j] = __int_as_float(0x7f800000);
+      }
+      continue;
+    }
+    // the lane holding the winner (keys are unique: global rows differ) emits and advances
+    if (best == wbest) {
+      uint32_t i = best_src / 32;
+      out_ids[q * k + j] = ids[((size_t)best_src * nq + q) * k + head[i]];
+      out_dist[q * k + j] = ord_f32((uint32_t)(wbest >> 32));
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t == (int)i) head[t]++;
+    }
+    ++cnt;
+  }
+  if (lane == 0 && out_counts) out_counts[q] = cnt;
+}
+
+int32_t merge_topk(const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq, uint32_t k,
+                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream) {
+  if (nq == 0) return SCN_OK;
+  if (n_shards == 0 || n_shards > 256) return fail(SCN_ERR_INVALID_PARAMETERS, "n_shards must be in [1, 256]");
+  merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(d_keys, d_ids, n_shards, nq, k, d_out_ids, d_out_dist,
+                                                                  d_out_counts);
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+}  // namespace scn

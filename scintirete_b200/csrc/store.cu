@@ -1,0 +1,497 @@
+// store.cu — device vector store + graph mirror + C-ABI plumbing (see include/scn_gpu.h).
+#include "store.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace scn {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  cudaGetLastError();
+  int32_t code = (e == cudaErrorMemoryAllocation) ? SCN_ERR_RESOURCE : SCN_ERR_INTERNAL;
+  return fail(code, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+}
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+cudaStream_t thread_stream(int device) {
+  // one non-blocking stream per (host thread, device): concurrent Search calls from different
+  // goroutines/threads overlap on the GPU (the reference allows concurrent readers, hnsw.go:293)
+  static thread_local cudaStream_t streams[64] = {};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!streams[device]) {
+    DeviceGuard g(device);
+    cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+  }
+  return streams[device];
+}
+
+void Profiler::collect() {
+  if (!on || ev.empty()) return;
+  cudaEventSynchronize(ev.back().second.second);
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->timing_names.clear();
+  s->timing_ms.clear();
+  for (auto& e : ev) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    s->timing_names.push_back(e.first);
+    s->timing_ms.push_back(ms);
+  }
+}
+
+Profiler::~Profiler() {
+  for (auto& e : ev) {
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+}
+
+// ---- row preparation (K6): norms, bf16 mirror, certificate bounds -----------------------------
+// One thread per row, strictly sequential over the row so that `norm` is bit-identical to the
+// reference's normB (distance.go:58-66) / VectorMagnitude (distance.go:175-181).
+template <int METRIC>
+__global__ void __launch_bounds__(128) prepare_rows_kernel(const float* __restrict__ vec, uint32_t pitch, uint32_t dim,
+                                                           uint32_t kpad, uint64_t first, uint64_t n,
+                                                           float* __restrict__ norm, __nv_bfloat16* __restrict__ mirror,
+                                                           float* __restrict__ aux, float* __restrict__ bounds) {
+  uint64_t r = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float mir_norm = 0.f, err_norm = 0.f, x_norm = 0.f;
+  if (r < first + n) {
+    const float* x = vec + r * pitch;
+    float ss = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) ss = __fadd_rn(ss, __fmul_rn(x[i], x[i]));
+    float nrm = __fsqrt_rn(ss);
+    norm[r] = nrm;
+    x_norm = nrm;
+    float inv = (METRIC == M_COS && nrm > 0.0f) ? (1.0f / nrm) : 1.0f;
+    float mm = 0.f, ee = 0.f;
+    __nv_bfloat16* mrow = mirror + r * kpad;
+    for (uint32_t i = 0; i < kpad; i += 8) {
+      __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = (i + j < dim) ? x[i + j] * inv : 0.0f;
+        __nv_bfloat16 b = __float2bfloat16_rn(v);
+        float bv = __bfloat162float(b);
+        mm = fmaf(bv, bv, mm);
+        ee = fmaf(v - bv, v - bv, ee);
+        out[j] = b;
+      }
+      *reinterpret_cast<uint4*>(mrow + i) = *reinterpret_cast<const uint4*>(out);
+    }
+    aux[r] = (METRIC == M_L2) ? mm : 0.0f;
+    mir_norm = sqrtf(mm) * 1.0000005f;
+    err_norm = sqrtf(ee) * 1.0000005f;
+  }
+  // block max -> global max (floats are non-negative: integer compare on the bits is monotone)
+  for (int o = 16; o > 0; o >>= 1) {
+    mir_norm = fmaxf(mir_norm, __shfl_xor_sync(0xffffffffu, mir_norm, o));
+    err_norm = fmaxf(err_norm, __shfl_xor_sync(0xffffffffu, err_norm, o));
+    x_norm = fmaxf(x_norm, __shfl_xor_sync(0xffffffffu, x_norm, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned int*>(bounds + 0), __float_as_uint(mir_norm));
+    atomicMax(reinterpret_cast<unsigned int*>(bounds + 1), __float_as_uint(err_norm));
+    if (x_norm == x_norm) atomicMax(reinterpret_cast<unsigned int*>(bounds + 2), __float_as_uint(x_norm));
+  }
+}
+
+int32_t launch_prepare_rows(scn_store* s, uint64_t first_row, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return SCN_OK;
+  dim3 grid((unsigned)((n + 127) / 128)), block(128);
+#define PREP(MT)                                                                                              \
+  prepare_rows_kernel<MT><<<grid, block, 0, stream>>>(s->d_vec, s->pitch, s->dim, s->kpad, first_row, n, s->d_norm, \
+                                                      s->d_mirror, s->d_aux, s->d_bounds)
+  switch (s->metric) {
+    case M_L2: PREP(M_L2); break;
+    case M_COS: PREP(M_COS); break;
+    default: PREP(M_IP); break;
+  }
+#undef PREP
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+uint64_t scn_store::device_bytes() const {
+  uint64_t b = cap * ((uint64_t)pitch * 4 + (uint64_t)kpad * 2 + 4 + 4 + 8) + (cap / 32 + 1) * 4 + 16;
+  if (has_graph) b += graph_nodes * ((uint64_t)2 * m * 4 + 1 + 4) + upper_lists * (uint64_t)m * 4;
+  return b;
+}
+
+template <class T>
+static int32_t grow(T** p, uint64_t old_count, uint64_t new_count, cudaStream_t st) {
+  T* np = nullptr;
+  SCN_CUDA(cudaMalloc(&np, std::max<uint64_t>(new_count, 1) * sizeof(T)));
+  if (*p && old_count) SCN_CUDA(cudaMemcpyAsync(np, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  if (new_count > old_count)
+    SCN_CUDA(cudaMemsetAsync(np + old_count, 0, (new_count - old_count) * sizeof(T), st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  if (*p) cudaFree(*p);
+  *p = np;
+  return SCN_OK;
+}
+
+static int32_t ensure_capacity(scn_store* s, uint64_t need) {
+  if (need <= s->cap) return SCN_OK;
+  if (need >= (uint64_t)ROW_NONE) return fail(SCN_ERR_RESOURCE, "store limited to 2^32-2 rows per device");
+  uint64_t nc = std::max<uint64_t>(need, s->cap + s->cap / 2);
+  nc = (nc + 255) / 256 * 256;
+  cudaStream_t st = thread_stream(s->device);
+  SCN_TRY(grow(&s->d_vec, s->rows * s->pitch, nc * s->pitch, st));
+  SCN_TRY(grow(&s->d_norm, s->rows, nc, st));
+  SCN_TRY(grow(&s->d_mirror, s->rows * s->kpad, nc * s->kpad, st));
+  SCN_TRY(grow(&s->d_aux, s->rows, nc, st));
+  SCN_TRY(grow(&s->d_ids, s->rows, nc, st));
+  SCN_TRY(grow(&s->d_deleted, (s->cap + 31) / 32, (nc + 31) / 32, st));
+  s->cap = nc;
+  return SCN_OK;
+}
+
+static void free_graph(scn_store* s) {
+  cudaFree(s->d_adj0);
+  cudaFree(s->d_levels);
+  cudaFree(s->d_up_off);
+  cudaFree(s->d_adj_up);
+  s->d_adj0 = s->d_up_off = s->d_adj_up = nullptr;
+  s->d_levels = nullptr;
+  s->has_graph = false;
+  s->max_layer = -1;
+  s->entry_id = 0;
+  s->entry_row = ROW_NONE;
+  s->graph_nodes = s->graph_edges = s->upper_lists = 0;
+}
+
+extern "C" {
+
+const char* scn_last_error(void) { return g_last_error.c_str(); }
+uint64_t scn_launch_count(void) { return g_launches.load(); }
+
+int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store** out) {
+  if (!out) return fail(SCN_ERR_INVALID_PARAMETERS, "out is NULL");
+  *out = nullptr;
+  if (metric != M_L2 && metric != M_COS && metric != M_IP)
+    return fail(SCN_ERR_INVALID_PARAMETERS, "unsupported distance metric");  // distance.go:138
+  if (dim == 0 || dim > 65536) return fail(SCN_ERR_INVALID_PARAMETERS, "dimension must be in [1, 65536]");
+  int ndev = 0;
+  SCN_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SCN_ERR_INVALID_PARAMETERS, "no CUDA device %d (have %d)", device, ndev);
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  SCN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SCN_ERR_INTERNAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  scn_store* s = new scn_store();
+  s->device = device;
+  s->dim = dim;
+  s->pitch = round_up(dim, 4);
+  s->kpad = round_up(dim, 64);
+  s->metric = metric;
+  if (cudaMalloc(&s->d_bounds, 4 * sizeof(float)) != cudaSuccess) {
+    delete s;
+    return cuda_fail(cudaGetLastError(), "cudaMalloc(bounds)", __FILE__, __LINE__);
+  }
+  cudaMemset(s->d_bounds, 0, 4 * sizeof(float));
+  *out = s;
+  return SCN_OK;
+}
+
+int32_t scn_store_destroy(scn_store* s) {
+  if (!s) return SCN_OK;
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  free_graph(s);
+  cudaFree(s->d_vec);
+  cudaFree(s->d_norm);
+  cudaFree(s->d_mirror);
+  cudaFree(s->d_aux);
+  cudaFree(s->d_ids);
+  cudaFree(s->d_deleted);
+  cudaFree(s->d_bounds);
+  delete s;
+  return SCN_OK;
+}
+
+int32_t scn_store_reserve(scn_store* s, uint64_t rows) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  DeviceGuard g(s->device);
+  return ensure_capacity(s, rows);
+}
+
+int32_t scn_store_clear(scn_store* s) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  free_graph(s);
+  s->rows = s->live = 0;
+  s->auto_ids = true;
+  s->row_of.clear();
+  if (s->d_deleted) SCN_CUDA(cudaMemset(s->d_deleted, 0, ((s->cap + 31) / 32) * 4));
+  SCN_CUDA(cudaMemset(s->d_bounds, 0, 4 * sizeof(float)));
+  return SCN_OK;
+}
+
+static int32_t append_common(scn_store* s, const float* src, bool src_on_device, const uint64_t* ids, uint64_t n) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  if (n == 0) return SCN_OK;
+  if (!src) return fail(SCN_ERR_INVALID_PARAMETERS, "vectors pointer is NULL");
+  DeviceGuard g(s->device);
+  // validate ids before touching anything (hnsw.go:192-194: duplicate -> error; id 0 is the
+  // reference's "no entrypoint" sentinel, hnsw.go:210/296)
+  std::vector<uint64_t> auto_buf;
+  if (ids) {
+    bool still_auto = s->auto_ids;
+    for (uint64_t i = 0; i < n && still_auto; ++i) still_auto = (ids[i] == s->rows + i + 1);
+    if (!still_auto) {
+      if (s->auto_ids) {  // materialise the implicit map
+        s->row_of.reserve((size_t)(s->rows + n) * 2);
+        for (uint64_t r = 0; r < s->rows; ++r) s->row_of[r + 1] = (uint32_t)r;
+        s->auto_ids = false;
+      }
+      for (uint64_t i = 0; i < n; ++i) {
+        if (ids[i] == 0) return fail(SCN_ERR_INVALID_PARAMETERS, "vector id 0 is reserved");
+        if (s->row_of.count(ids[i]))
+          return fail(SCN_ERR_INVALID_PARAMETERS, "vector with ID %llu already exists", (unsigned long long)ids[i]);
+      }
+      // duplicates inside the batch
+      for (uint64_t i = 0; i < n; ++i) {
+        auto ins = s->row_of.emplace(ids[i], (uint32_t)(s->rows + i));
+        if (!ins.second) {
+          for (uint64_t j = 0; j < i; ++j) s->row_of.erase(ids[j]);
+          return fail(SCN_ERR_INVALID_PARAMETERS, "vector with ID %llu already exists", (unsigned long long)ids[i]);
+        }
+      }
+    }
+  } else {
+    if (!s->auto_ids) {
+      // explicit ids were used before: auto ids continue from row+1 only if free
+      for (uint64_t i = 0; i < n; ++i)
+        if (s->row_of.count(s->rows + i + 1))
+          return fail(SCN_ERR_INVALID_PARAMETERS, "auto id %llu collides with an explicit id",
+                      (unsigned long long)(s->rows + i + 1));
+      for (uint64_t i = 0; i < n; ++i) s->row_of[s->rows + i + 1] = (uint32_t)(s->rows + i);
+    }
+    auto_buf.resize(n);
+    for (uint64_t i = 0; i < n; ++i) auto_buf[i] = s->rows + i + 1;
+    ids = auto_buf.data();
+  }
+  int32_t rc = ensure_capacity(s, s->rows + n);
+  if (rc != SCN_OK) {
+    if (!s->auto_ids)
+      for (uint64_t i = 0; i < n; ++i) s->row_of.erase(ids[i]);
+    return rc;
+  }
+  cudaStream_t st = thread_stream(s->device);
+  cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  float* dst = s->d_vec + s->rows * s->pitch;
+  if (s->pitch == s->dim) {
+    SCN_CUDA(cudaMemcpyAsync(dst, src, n * s->dim * sizeof(float), kind, st));
+  } else {
+    SCN_CUDA(cudaMemsetAsync(dst, 0, n * s->pitch * sizeof(float), st));
+    SCN_CUDA(cudaMemcpy2DAsync(dst, s->pitch * sizeof(float), src, s->dim * sizeof(float), s->dim * sizeof(float), n,
+                               kind, st));
+  }
+  SCN_CUDA(cudaMemcpyAsync(s->d_ids + s->rows, ids, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  SCN_TRY(launch_prepare_rows(s, s->rows, n, st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  s->rows += n;
+  s->live += n;
+  return SCN_OK;
+}
+
+int32_t scn_store_append(scn_store* s, const float* vecs, const uint64_t* ids, uint64_t n) {
+  return append_common(s, vecs, false, ids, n);
+}
+int32_t scn_store_append_dev(scn_store* s, const float* d_vecs, const uint64_t* ids, uint64_t n) {
+  return append_common(s, d_vecs, true, ids, n);
+}
+
+int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  if (n == 0) return SCN_OK;
+  DeviceGuard g(s->device);
+  std::vector<uint32_t> rows(n);
+  for (uint64_t i = 0; i < n; ++i)
+    if (!s->lookup(ids[i], &rows[i]))
+      return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);  // hnsw.go:271-273
+  // read-modify-write of the bitmap words on the host side of the mirror (mutators are exclusive)
+  size_t words = (s->rows + 31) / 32;
+  std::vector<uint32_t> bits(words);
+  cudaStream_t st = thread_stream(s->device);
+  SCN_CUDA(cudaMemcpyAsync(bits.data(), s->d_deleted, words * 4, cudaMemcpyDeviceToHost, st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t r : rows) {
+    uint32_t& w = bits[r >> 5];
+    uint32_t b = 1u << (r & 31);
+    if (!(w & b)) {  // already deleted -> no-op (hnsw.go:275-277)
+      w |= b;
+      s->live--;
+    }
+  }
+  SCN_CUDA(cudaMemcpyAsync(s->d_deleted, bits.data(), words * 4, cudaMemcpyHostToDevice, st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  return SCN_OK;
+}
+
+int32_t scn_store_stats(scn_store* s, scn_stats* out) {
+  if (!s || !out) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  std::memset(out, 0, sizeof *out);
+  out->rows = s->rows;
+  out->live_rows = s->live;
+  out->capacity_rows = s->cap;
+  out->device_bytes = s->device_bytes();
+  out->dim = s->dim;
+  out->metric = s->metric;
+  out->device = s->device;
+  out->has_graph = s->has_graph ? 1 : 0;
+  out->max_layer = s->max_layer;
+  out->m = s->m;
+  out->entry_id = s->entry_id;
+  out->graph_edges = s->graph_edges;
+  return SCN_OK;
+}
+
+int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, float* out) {
+  if (!s || (!ids && n) || (!out && n)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  DeviceGuard g(s->device);
+  cudaStream_t st = thread_stream(s->device);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t r;
+    if (!s->lookup(ids[i], &r)) return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);
+    SCN_CUDA(cudaMemcpyAsync(out + i * s->dim, s->d_vec + (uint64_t)r * s->pitch, s->dim * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  }
+  SCN_CUDA(cudaStreamSynchronize(st));
+  return SCN_OK;
+}
+
+int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t entry_id, uint64_t n_nodes,
+                         const uint64_t* node_ids, const int32_t* list_counts, const uint32_t* edge_counts,
+                         const uint64_t* edges) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  if (m <= 0 || m > 512) return fail(SCN_ERR_INVALID_PARAMETERS, "M must be in [1, 512]");
+  if (n_nodes && (!node_ids || !list_counts || !edge_counts)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  const uint32_t s0 = 2 * (uint32_t)m, su = (uint32_t)m;
+  uint64_t n = s->rows;
+  std::vector<uint32_t> adj0((size_t)n * s0, ROW_NONE);
+  std::vector<uint8_t> levels(n, 0);
+  std::vector<uint32_t> up_off(n, 0);
+  // first pass: rows, levels, upper offsets
+  std::vector<uint32_t> node_row(n_nodes);
+  uint64_t upper = 0;
+  for (uint64_t i = 0; i < n_nodes; ++i) {
+    uint32_t r;
+    if (!s->lookup(node_ids[i], &r))
+      return fail(SCN_ERR_INDEX_BUILD_FAILED, "graph node %llu is not in the store", (unsigned long long)node_ids[i]);
+    node_row[i] = r;
+    int lc = list_counts[i];
+    if (lc < 0 || lc > 255) return fail(SCN_ERR_INVALID_PARAMETERS, "node %llu has %d layers", (unsigned long long)node_ids[i], lc);
+    levels[r] = (uint8_t)(lc > 0 ? lc - 1 : 0);
+    up_off[r] = (uint32_t)upper;
+    if (lc > 1) upper += (uint64_t)(lc - 1);
+  }
+  if (upper >= 0xFFFFFFFFull) return fail(SCN_ERR_RESOURCE, "too many upper-layer lists");
+  std::vector<uint32_t> adj_up((size_t)upper * su, ROW_NONE);
+  uint64_t li = 0, ei = 0, total_edges = 0;
+  for (uint64_t i = 0; i < n_nodes; ++i) {
+    uint32_t r = node_row[i];
+    for (int l = 0; l < list_counts[i]; ++l) {
+      uint32_t c = edge_counts[li++];
+      uint32_t cap_l = (l == 0) ? s0 : su;
+      if (c > cap_l)
+        return fail(SCN_ERR_INVALID_PARAMETERS, "node %llu layer %d has %u neighbours (max %u)",
+                    (unsigned long long)node_ids[i], l, c, cap_l);
+      uint32_t* dst = (l == 0) ? &adj0[(size_t)r * s0] : &adj_up[((size_t)up_off[r] + (l - 1)) * su];
+      for (uint32_t e = 0; e < c; ++e) {
+        uint32_t nr;
+        if (!s->lookup(edges[ei + e], &nr))
+          return fail(SCN_ERR_INDEX_BUILD_FAILED, "neighbour %llu of node %llu is not in the store",
+                      (unsigned long long)edges[ei + e], (unsigned long long)node_ids[i]);
+        dst[e] = nr;
+      }
+      ei += c;
+      total_edges += c;
+    }
+  }
+  uint32_t entry_row = ROW_NONE;
+  if (entry_id != 0 && !s->lookup(entry_id, &entry_row))
+    return fail(SCN_ERR_INDEX_BUILD_FAILED, "entrypoint %llu is not in the store", (unsigned long long)entry_id);
+  free_graph(s);
+  SCN_CUDA(cudaMalloc(&s->d_adj0, std::max<size_t>(adj0.size(), 1) * 4));
+  SCN_CUDA(cudaMalloc(&s->d_levels, std::max<size_t>(levels.size(), 1)));
+  SCN_CUDA(cudaMalloc(&s->d_up_off, std::max<size_t>(up_off.size(), 1) * 4));
+  SCN_CUDA(cudaMalloc(&s->d_adj_up, std::max<size_t>(adj_up.size(), 1) * 4));
+  SCN_CUDA(cudaMemcpy(s->d_adj0, adj0.data(), adj0.size() * 4, cudaMemcpyHostToDevice));
+  SCN_CUDA(cudaMemcpy(s->d_levels, levels.data(), levels.size(), cudaMemcpyHostToDevice));
+  SCN_CUDA(cudaMemcpy(s->d_up_off, up_off.data(), up_off.size() * 4, cudaMemcpyHostToDevice));
+  SCN_CUDA(cudaMemcpy(s->d_adj_up, adj_up.data(), adj_up.size() * 4, cudaMemcpyHostToDevice));
+  s->has_graph = true;
+  s->m = m;
+  s->max_layer = max_layer;
+  s->entry_id = entry_id;
+  s->entry_row = entry_row;
+  s->graph_nodes = n;
+  s->graph_edges = total_edges;
+  s->upper_lists = upper;
+  return SCN_OK;
+}
+
+int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
+  if (!s || !name) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  std::string n(name);
+  if (n == "flat_path") {
+    if (value < 0 || value > 2) return fail(SCN_ERR_INVALID_PARAMETERS, "flat_path must be 0, 1 or 2");
+    s->opt_flat_path = value;
+  } else if (n == "tensor_min_batch") {
+    s->opt_tensor_min_batch = value;
+  } else if (n == "overfetch") {
+    s->opt_overfetch = value;
+  } else if (n == "profile") {
+    s->opt_profile = value;
+  } else {
+    return fail(SCN_ERR_INVALID_PARAMETERS, "unknown option '%s'", name);
+  }
+  return SCN_OK;
+}
+
+int32_t scn_last_timings(scn_store* s, const char** names, float* ms, int32_t max_entries) {
+  if (!s) return 0;
+  std::lock_guard<std::mutex> lk(s->mu);
+  int32_t n = (int32_t)std::min<size_t>(s->timing_names.size(), (size_t)std::max(0, max_entries));
+  for (int32_t i = 0; i < n; ++i) {
+    if (names) names[i] = s->timing_names[i].c_str();
+    if (ms) ms[i] = s->timing_ms[i];
+  }
+  return n;
+}
+
+int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n) {
+  if (!s || !out) return 0;
+  std::lock_guard<std::mutex> lk(s->mu);
+  int32_t m = std::min(n, 4);
+  for (int32_t i = 0; i < m; ++i) out[i] = s->counters[i];
+  return m;
+}
+
+}  // extern "C"

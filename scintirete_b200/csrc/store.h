@@ -1,0 +1,168 @@
+// store.h — device-memory mirror of the reference's node store (hnsw.go:17-26, 115) on one GPU.
+//
+// HBM layout (rows in insertion order; row == id-1 for auto-assigned ids, collection.go:115-116):
+//   vec      float   [cap][pitch]     fp32 rows, pitch = dim rounded up to 4 floats, zero padded
+//   norm     float   [cap]            ||x|| in the reference's sequential fp32 order (cosine normB)
+//   mirror   bf16    [cap][kpad]      tensor-core operand: bf16(x) (L2, IP) or bf16(x/||x||) (cosine),
+//                                     kpad = dim rounded up to 64, zero padded
+//   aux      float   [cap]            filter-side per-row term: sum(mirror^2) for L2, else unused (0)
+//   ids      u64     [cap]            external id of each row
+//   deleted  u32     [cap/32]         soft-delete bitmap (HNSWNode.Deleted)
+//   adj0     u32     [n][2M]          layer-0 neighbour rows, ROW_NONE padded (one 128 B line at M=16)
+//   levels   u8      [n]              len(Connections)-1
+//   up_off   u32     [n]              first upper-layer list of the node (in lists), for level >= 1
+//   adj_up   u32     [lists][M]       upper-layer neighbour rows, ROW_NONE padded
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+struct scn_store {
+  int32_t device = 0;
+  uint32_t dim = 0;
+  uint32_t pitch = 0;  // floats per fp32 row
+  uint32_t kpad = 0;   // bf16 elements per mirror row
+  int32_t metric = 0;
+
+  uint64_t rows = 0, cap = 0, live = 0;
+  float* d_vec = nullptr;
+  float* d_norm = nullptr;
+  __nv_bfloat16* d_mirror = nullptr;
+  float* d_aux = nullptr;
+  uint64_t* d_ids = nullptr;
+  uint32_t* d_deleted = nullptr;
+  // running maxima over rows, for the tensor-path certificate (device float[4]):
+  //   [0] max ||mirror row||   [1] max ||x_true - mirror row||   [2] max ||x||   [3] reserved
+  float* d_bounds = nullptr;
+
+  bool auto_ids = true;  // every id so far was row+1 -> no host map needed
+  std::unordered_map<uint64_t, uint32_t> row_of;
+
+  // graph
+  bool has_graph = false;
+  int32_t m = 0, max_layer = -1;
+  uint64_t entry_id = 0;
+  uint32_t entry_row = scn::ROW_NONE;
+  uint64_t graph_nodes = 0, graph_edges = 0, upper_lists = 0;
+  uint32_t* d_adj0 = nullptr;
+  uint8_t* d_levels = nullptr;
+  uint32_t* d_up_off = nullptr;
+  uint32_t* d_adj_up = nullptr;
+
+  // options
+  int64_t opt_flat_path = 0;
+  int64_t opt_tensor_min_batch = 16;
+  int64_t opt_overfetch = 0;  // 0 = auto
+  int64_t opt_profile = 0;
+
+  // introspection (protected by mu)
+  std::mutex mu;
+  std::vector<std::string> timing_names;
+  std::vector<float> timing_ms;
+  uint64_t counters[4] = {0, 0, 0, 0};
+
+  uint64_t device_bytes() const;
+  bool lookup(uint64_t id, uint32_t* row) const {
+    if (auto_ids) {
+      if (id == 0 || id > rows) return false;
+      *row = (uint32_t)(id - 1);
+      return true;
+    }
+    auto it = row_of.find(id);
+    if (it == row_of.end()) return false;
+    *row = it->second;
+    return true;
+  }
+};
+
+namespace scn {
+
+// RAII device guard
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Stream-ordered scratch allocation tied to a call.
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  template <class T>
+  int32_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, count * sizeof(T) + 16, stream);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return scn::fail(SCN_ERR_RESOURCE, "device scratch allocation of %zu bytes failed: %s", count * sizeof(T),
+                       cudaGetErrorString(e));
+    }
+    ptrs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return SCN_OK;
+  }
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+};
+
+// Optional per-kernel CUDA-event timing on the launching stream.
+struct Profiler {
+  scn_store* s;
+  cudaStream_t stream;
+  bool on;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+  Profiler(scn_store* st, cudaStream_t str) : s(st), stream(str), on(st && st->opt_profile != 0) {}
+  void begin(const char* name) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, stream);
+    ev.push_back({name, {a, b}});
+  }
+  void end() {
+    if (!on) return;
+    cudaEventRecord(ev.back().second.second, stream);
+  }
+  // requires the stream to be synchronised by the caller (or syncs on the last event)
+  void collect();
+  ~Profiler();
+};
+
+cudaStream_t thread_stream(int device);
+
+// kernels / launchers implemented in the other translation units
+int32_t launch_prepare_rows(scn_store* s, uint64_t first_row, uint64_t n, cudaStream_t stream);
+
+int32_t flat_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlist, const uint32_t* d_nq_dev,
+                          uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream,
+                          Profiler* prof);
+int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64_t row_base, uint64_t* d_out_ids,
+                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream);
+int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
+                           uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof);
+bool tensor_path_supported(const scn_store* s, uint32_t k);
+int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand,
+                    uint32_t k, uint64_t* d_out_keys, cudaStream_t stream);
+int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                    float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, Profiler* prof);
+int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const float* d_x, uint64_t nx, uint32_t dim,
+                       float* d_out, cudaStream_t stream);
+int32_t merge_topk(const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq, uint32_t k,
+                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream);
+
+}  // namespace scn

@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's index/distance interfaces for the search hot path.
+
+Same names, argument meaning and error behaviour as internal/core/interfaces.go
+(VectorIndex 87-111, HNSWIndex 114-134, DistanceCalculator 154-163, IndexFactory 187-196) and
+internal/core/algorithm/distance.go, on top of the C ABI in include/scn_gpu.h. This is what the Go
+`GPUIndex` in go/ does through cgo; Go is not installed in this image, so this Python twin is the
+tested binding. All arithmetic happens on the GPU: there is no CPU fallback anywhere in here.
+
+Graph construction (HNSW.Insert/Build: searchLayer with efConstruction, selectNeighbors,
+pruneConnections — hnsw.go:190-257, 560-614) stays with the reference's CPU implementation; the
+built graph is handed over with ``import_graph_state`` exactly as persistence does on restore
+(database.go:398-493 -> hnsw.go:749-804).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+from .types import (DistanceMetric, ErrorCode, GraphState, HNSWParams, ScintireteError, SearchParams, SearchResult,
+                    Vector)
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise ScintireteError(rc, _native.last_error())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---- DistanceCalculator (distance.go) --------------------------------------------------------
+
+class DistanceCalculator:
+    """core.DistanceCalculator backed by scn_distance_batch (exact reference arithmetic on GPU)."""
+
+    def __init__(self, metric: DistanceMetric, device: int = 0):
+        self._metric = DistanceMetric(metric)
+        self._device = device
+
+    def distance(self, a, b) -> np.float32:
+        a, b = _f32(a).ravel(), _f32(b).ravel()
+        if a.size != b.size:  # distance.go:22-24: +Inf, not an error
+            return np.float32(np.inf)
+        return self.pairwise(a[None, :], b[None, :])[0, 0]
+
+    def pairwise(self, queries, targets) -> np.ndarray:
+        q, x = _f32(queries), _f32(targets)
+        if q.shape[1] != x.shape[1]:
+            return np.full((q.shape[0], x.shape[0]), np.inf, np.float32)
+        out = np.empty((q.shape[0], x.shape[0]), np.float32)
+        _check(_native.lib().scn_distance_batch(self._device, int(self._metric), _ptr(q), q.shape[0], _ptr(x), x.shape[0],
+                                                q.shape[1], _ptr(out)))
+        return out
+
+    def distance_type(self) -> DistanceMetric:
+        return self._metric
+
+    def is_similarity(self) -> bool:  # distance.go:40-42, 90-92, 124-126
+        return False
+
+
+def new_distance_calculator(metric, device: int = 0) -> DistanceCalculator:
+    """algorithm.NewDistanceCalculator (distance.go:129-140)."""
+    try:
+        m = DistanceMetric(metric)
+    except ValueError:
+        m = DistanceMetric.UNSPECIFIED
+    if m == DistanceMetric.UNSPECIFIED:
+        raise ScintireteError(ErrorCode.INVALID_PARAMETERS, "unsupported distance metric")
+    return DistanceCalculator(m, device)
+
+
+def batch_distance(calc: DistanceCalculator, query, targets) -> np.ndarray:
+    """algorithm.BatchDistance (distance.go:144-150)."""
+    t = _f32(targets)
+    if t.shape[0] == 0:
+        return np.empty(0, np.float32)
+    return calc.pairwise(_f32(query)[None, :], t)[0]
+
+
+# ---- device store ------------------------------------------------------------------------------
+
+class DeviceStore:
+    """Owns one scn_store (device-memory mirror of the node store, hnsw.go:17-26,115)."""
+
+    def __init__(self, dim: int, metric: DistanceMetric, device: int = 0):
+        h = C.c_void_p()
+        _check(_native.lib().scn_store_create(device, dim, int(metric), C.byref(h)))
+        self._h = h
+        self.dim, self.metric, self.device = dim, DistanceMetric(metric), device
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _native.lib().scn_store_destroy(h)
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def reserve(self, rows: int):
+        _check(_native.lib().scn_store_reserve(self._h, rows))
+
+    def clear(self):
+        _check(_native.lib().scn_store_clear(self._h))
+
+    def append(self, vectors, ids=None):
+        v = _f32(vectors)
+        if v.ndim == 1:
+            v = v[None, :]
+        if v.shape[1] != self.dim:
+            raise ScintireteError(ErrorCode.DIMENSION_MISMATCH, f"vector has dimension {v.shape[1]}, expected {self.dim}")
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        _check(_native.lib().scn_store_append(self._h, _ptr(v), _ptr(ids_a), v.shape[0]))
+
+    def append_device(self, data_ptr: int, n: int, ids=None):
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        _check(_native.lib().scn_store_append_dev(self._h, C.c_void_p(data_ptr), _ptr(ids_a), n))
+
+    def mark_deleted(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
+        _check(_native.lib().scn_store_mark_deleted(self._h, _ptr(a), a.size))
+
+    def stats(self) -> _native.Stats:
+        st = _native.Stats()
+        _check(_native.lib().scn_store_stats(self._h, C.byref(st)))
+        return st
+
+    def get(self, ids) -> np.ndarray:
+        a = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
+        out = np.empty((a.size, self.dim), np.float32)
+        _check(_native.lib().scn_store_get(self._h, _ptr(a), a.size, _ptr(out)))
+        return out
+
+    def graph_upload(self, st: GraphState):
+        ids = np.ascontiguousarray(st.node_ids, dtype=np.uint64)
+        lc = np.ascontiguousarray(st.list_counts, dtype=np.int32)
+        ec = np.ascontiguousarray(st.edge_counts, dtype=np.uint32)
+        ed = np.ascontiguousarray(st.edges, dtype=np.uint64)
+        _check(_native.lib().scn_graph_upload(self._h, st.m, st.max_layer, st.entry_point, ids.size, _ptr(ids), _ptr(lc),
+                                              _ptr(ec), _ptr(ed)))
+
+    def set_option(self, name: str, value: int):
+        _check(_native.lib().scn_set_option(self._h, name.encode(), value))
+
+    def last_timings(self) -> Dict[str, float]:
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = _native.lib().scn_last_timings(self._h, names, ms, 32)
+        out: Dict[str, float] = {}
+        for i in range(n):
+            key = names[i].decode()
+            out[key] = out.get(key, 0.0) + float(ms[i])
+        return out
+
+    def last_counters(self) -> List[int]:
+        c = (C.c_uint64 * 4)()
+        n = _native.lib().scn_last_counters(self._h, c, 4)
+        return [int(c[i]) for i in range(n)]
+
+    # -- search, host buffers (the call a Go Collection.Search would make) --
+    def _prep(self, queries, k):
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise ScintireteError(ErrorCode.DIMENSION_MISMATCH,
+                                  f"query has dimension {q.shape[1]}, expected {self.dim}")
+        nq = q.shape[0]
+        return q, np.zeros((nq, k), np.uint64), np.full((nq, k), np.inf, np.float32), np.zeros(nq, np.uint32)
+
+    def search_flat(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        q, ids, dist, cnt = self._prep(queries, max(k, 1))
+        _check(_native.lib().scn_search_flat(self._h, _ptr(q), q.shape[0], k, _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, cnt
+
+    def search_hnsw(self, queries, k: int, ef: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        q, ids, dist, cnt = self._prep(queries, max(k, 1))
+        _check(_native.lib().scn_search_hnsw(self._h, _ptr(q), q.shape[0], k, ef, _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, cnt
+
+    def rerank(self, queries, cand_ids, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        q, ids, dist, cnt = self._prep(queries, max(k, 1))
+        c = np.ascontiguousarray(cand_ids, dtype=np.uint64)
+        if c.ndim == 1:
+            c = c[None, :]
+        _check(_native.lib().scn_rerank(self._h, _ptr(q), q.shape[0], _ptr(c), c.shape[1], k, _ptr(ids), _ptr(dist),
+                                        _ptr(cnt)))
+        return ids, dist, cnt
+
+
+# ---- VectorIndex / HNSWIndex ---------------------------------------------------------------------
+
+class _GPUIndexBase:
+    """Shared VectorIndex plumbing (interfaces.go:87-111)."""
+
+    def __init__(self, dim: int, metric, device: int = 0):
+        try:
+            m = DistanceMetric(metric)
+        except ValueError:
+            m = DistanceMetric.UNSPECIFIED
+        if m == DistanceMetric.UNSPECIFIED:  # NewHNSW -> NewDistanceCalculator error (hnsw.go:129-132)
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, "unsupported distance metric")
+        self.metric = m
+        self.dim = dim
+        self.store = DeviceStore(dim, m, device)
+        self._metadata: Dict[int, Dict[str, Any]] = {}
+        self._deleted: set = set()
+
+    # -- mutation --
+    def insert(self, vector: Vector) -> None:
+        e = _f32(vector.elements)
+        if vector.id == 0 or self._has(vector.id):
+            raise ScintireteError(ErrorCode.INSERT_FAILED, f"failed to insert vector {vector.id}")  # hnsw.go:181-183
+        self.store.append(e[None, :], [vector.id])
+        if vector.metadata:
+            self._metadata[vector.id] = vector.metadata
+
+    def _has(self, id_: int) -> bool:
+        try:
+            self.store.get([id_])
+            return True
+        except ScintireteError:
+            return False
+
+    def delete(self, id_: str) -> None:
+        try:
+            vid = int(str(id_).strip())  # hnsw.go:265-268 Sscanf("%d")
+        except ValueError:
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, f"invalid ID format: {id_}")
+        self.store.mark_deleted([vid])
+        self._deleted.add(vid)
+
+    # -- read --
+    def get(self, id_: str) -> Vector:
+        try:
+            vid = int(str(id_).strip())
+        except ValueError:
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, f"invalid ID format: {id_}")
+        if vid in self._deleted:
+            raise ScintireteError(ErrorCode.VECTOR_NOT_FOUND, f"vector {id_} not found")  # hnsw.go:364-366
+        return Vector(vid, self.store.get([vid])[0], self._metadata.get(vid))
+
+    def size(self) -> int:
+        return int(self.store.stats().live_rows)
+
+    def memory_usage(self) -> int:
+        return int(self.store.stats().device_bytes)
+
+    def _results(self, ids, dist, cnt, include_vector: bool) -> List[List[SearchResult]]:
+        out = []
+        for qi in range(ids.shape[0]):
+            n = int(cnt[qi])
+            vecs = self.store.get(ids[qi, :n]) if (include_vector and n) else None
+            out.append([SearchResult(Vector(int(ids[qi, j]), None if vecs is None else vecs[j],
+                                            self._metadata.get(int(ids[qi, j]))), float(dist[qi, j])) for j in range(n)])
+        return out
+
+
+class GPUFlatIndex(_GPUIndexBase):
+    """Exact-scan VectorIndex ("flat-gpu"): BatchDistance + stable sort, on the GPU."""
+
+    def build(self, vectors: Sequence[Vector]) -> None:  # VectorIndex.Build: clear, then insert all
+        self.store.clear()
+        self._metadata.clear()
+        self._deleted.clear()
+        if len(vectors):
+            self.store.append(np.stack([_f32(v.elements) for v in vectors]), [v.id for v in vectors])
+            for v in vectors:
+                if v.metadata:
+                    self._metadata[v.id] = v.metadata
+
+    def search_batch(self, queries, params: SearchParams):
+        if params.top_k <= 0:
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, "top_k must be positive")
+        return self.store.search_flat(queries, params.top_k)
+
+    def search(self, query, params: SearchParams, include_vector: bool = False) -> List[SearchResult]:
+        return self._results(*self.search_batch(_f32(query)[None, :], params), include_vector)[0]
+
+    def get_statistics(self):
+        st = self.store.stats()
+        return {"nodes": int(st.live_rows), "memory_usage": int(st.device_bytes)}
+
+
+class GPUHNSWIndex(_GPUIndexBase):
+    """core.HNSWIndex ("hnsw-gpu") whose Search runs on the GPU over a graph built by the
+    reference algorithm and handed over via import_graph_state."""
+
+    def __init__(self, params: HNSWParams, metric, dim: int, device: int = 0):
+        super().__init__(dim, metric, device)
+        self.params = params
+        self._graph: Optional[GraphState] = None
+
+    def build(self, vectors: Sequence[Vector]) -> None:
+        raise ScintireteError(ErrorCode.INDEX_BUILD_FAILED,
+                              "graph construction stays with the host HNSW (hnsw.go:148-257); "
+                              "hand the built graph over with import_graph_state")
+
+    def get_parameters(self) -> HNSWParams:
+        return self.params
+
+    def set_ef_search(self, ef_search: int) -> None:  # hnsw.go:449-453
+        self.params.ef_search = ef_search
+
+    def get_layers(self) -> int:  # hnsw.go:394-401
+        ml = self.store.stats().max_layer
+        return 0 if ml < 0 else ml + 1
+
+    def import_graph_state(self, state: GraphState) -> None:
+        """hnsw.go:749-804: replace all nodes, then take entrypoint / maxLayer / size verbatim."""
+        if state.vectors is None:
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, "graph state carries no vectors")
+        self.store.clear()
+        self._deleted.clear()
+        self.store.append(state.vectors, state.node_ids)
+        self.store.graph_upload(state)
+        if state.deleted is not None and np.any(state.deleted):
+            dead = np.asarray(state.node_ids)[np.asarray(state.deleted).astype(bool)]
+            self.store.mark_deleted(dead)
+            self._deleted.update(int(x) for x in dead)
+        self._graph = state
+
+    def export_graph_state(self) -> Optional[GraphState]:
+        return self._graph
+
+    def get_graph_statistics(self):  # hnsw.go:404-443
+        st = self.store.stats()
+        live = int(st.live_rows)
+        return {"layers": int(st.max_layer) + 1, "nodes": live, "connections": int(st.graph_edges),
+                "avg_degree": (st.graph_edges / live) if live else 0.0, "memory_usage": int(st.device_bytes)}
+
+    get_statistics = get_graph_statistics
+
+    def _ef(self, params: SearchParams) -> int:  # hnsw.go:300-303
+        if params.ef_search is not None and params.ef_search > 0:
+            return params.ef_search
+        return self.params.ef_search
+
+    def search_batch(self, queries, params: SearchParams):
+        if params.top_k <= 0:
+            raise ScintireteError(ErrorCode.INVALID_PARAMETERS, "top_k must be positive")
+        return self.store.search_hnsw(queries, params.top_k, self._ef(params))
+
+    def search(self, query, params: SearchParams, include_vector: bool = False) -> List[SearchResult]:
+        return self._results(*self.search_batch(_f32(query)[None, :], params), include_vector)[0]
+
+    def search_exact(self, queries, params: SearchParams):
+        """Flat ground truth over the same rows (SURVEY.md §8b `SearchExact`)."""
+        return self.store.search_flat(queries, params.top_k)
+
+
+class IndexFactory:
+    """core.IndexFactory (interfaces.go:187-196) for the two GPU index types."""
+
+    def __init__(self, device: int = 0):
+        self.device = device
+
+    def create_index(self, config: Dict[str, Any]):
+        kind = config.get("type", "hnsw-gpu")
+        metric, dim = config["metric"], config["dim"]
+        if kind == "flat-gpu":
+            return GPUFlatIndex(dim, metric, self.device)
+        if kind == "hnsw-gpu":
+            p = config.get("parameters", {})
+            hp = HNSWParams(**{k: p[k] for k in ("m", "ef_construction", "ef_search", "max_layers", "seed") if k in p})
+            return GPUHNSWIndex(hp, metric, dim, self.device)
+        raise ScintireteError(ErrorCode.INVALID_PARAMETERS, f"unsupported index type {kind}")
+
+    def supported_metrics(self) -> List[DistanceMetric]:
+        return [DistanceMetric.L2, DistanceMetric.COSINE, DistanceMetric.INNER_PRODUCT]
+
+    def default_parameters(self) -> Dict[str, Any]:
+        return {"m": 16, "ef_construction": 200, "ef_search": 50, "max_layers": 16}

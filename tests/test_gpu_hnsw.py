@@ -1,0 +1,114 @@
+"""GPU parity: batched HNSW search over the oracle-built graph (the graph the reference's
+algorithm builds) vs the oracle's own Search on the same graph, same queries, same ef.
+Bar (north_star): recall@10 within 0.5 % absolute of the reference at equal efSearch; returned
+distances must be the exact reference arithmetic for the returned ids."""
+import numpy as np
+import pytest
+
+import oracle
+from scintirete_b200 import DistanceMetric, GPUHNSWIndex, HNSWParams, ScintireteError, SearchParams
+from util import gaussian, recall, to_graph_state
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(metric, n, d, M=16, efc=200, seed=42, max_layers=16):
+    db = gaussian(n, d, 1234)
+    h = oracle.OracleHNSW(M=M, ef_construction=efc, ef_search=50, max_layers=max_layers, seed=seed, metric=int(metric))
+    h.build(db)
+    g = GPUHNSWIndex(HNSWParams(m=M, ef_construction=efc, ef_search=50, max_layers=max_layers, seed=seed), metric, d)
+    g.import_graph_state(to_graph_state(h.export_graph_state(), M))
+    return db, h, g
+
+
+@pytest.mark.parametrize("metric", [DistanceMetric.L2, DistanceMetric.COSINE, DistanceMetric.INNER_PRODUCT])
+def test_recall_parity_and_exact_distances(metric):
+    n, d, nq, k, ef = 8000, 64, 200, 10, 100
+    db, h, g = _pair(metric, n, d)
+    q = gaussian(nq, d, 4321)
+    gt, _, _ = oracle.flat_search(int(metric), db, q, k, nthreads=8)
+    o_ids, o_dist, o_cnt, _ = h.search_batch(q, k, ef, nthreads=8)
+    ids, dist, cnt = g.search_batch(q, SearchParams(top_k=k, ef_search=ef))
+    r_gpu, r_ref = recall(ids, gt), recall(o_ids, gt)
+    assert abs(r_gpu - r_ref) <= 0.005, (r_gpu, r_ref)
+    assert np.array_equal(cnt, o_cnt)
+    # exact-set agreement with the oracle (expected ~1: only float near-ties can reorder the walk)
+    agree = recall(ids, o_ids)
+    assert agree >= 0.99, agree
+    # every returned distance is the reference's exact arithmetic for that id, list sorted ascending
+    for i in range(0, nq, 17):
+        want = oracle.batch_distance(int(metric), q[i], db[ids[i].astype(np.int64) - 1])
+        assert np.array_equal(dist[i], want)
+        assert np.all(np.diff(dist[i]) >= 0)
+
+
+def test_c1_shape_small_and_default_ef():
+    # C1 shape (128-d L2, M=16, efC=200, efS=100) at a size the oracle builds in seconds
+    n, d, nq, k = 6000, 128, 100, 10
+    db, h, g = _pair(DistanceMetric.L2, n, d)
+    q = gaussian(nq, d, 4321)
+    h.set_ef_search(100)
+    g.set_ef_search(100)
+    o_ids, _, _, _ = h.search_batch(q, k, None, nthreads=8)
+    ids, _, _ = g.search_batch(q, SearchParams(top_k=k))
+    gt, _, _ = oracle.flat_search(1, db, q, k, nthreads=8)
+    assert abs(recall(ids, gt) - recall(o_ids, gt)) <= 0.005
+
+
+def test_topk_larger_than_ef_and_k1():
+    db, h, g = _pair(DistanceMetric.L2, 2000, 16)
+    q = gaussian(20, 16, 7)
+    ids, dist, cnt = g.search_batch(q, SearchParams(top_k=50, ef_search=7))
+    assert np.all(cnt == 7) and np.all(ids[:, 7:] == 0) and np.all(np.isinf(dist[:, 7:]))
+    o_ids, _, o_cnt, _ = h.search_batch(q, 50, 7)
+    assert np.array_equal(cnt, o_cnt) and recall(ids[:, :7], o_ids[:, :7]) >= 0.97
+    ids1, _, _ = g.search_batch(q, SearchParams(top_k=1, ef_search=1))
+    o1, _, _, _ = h.search_batch(q, 1, 1)
+    assert np.mean(ids1 == o1) >= 0.95
+
+
+def test_deleted_nodes_are_walls():
+    db, h, g = _pair(DistanceMetric.L2, 3000, 24)
+    dead = np.arange(2, 3000, 5).astype(np.uint64)
+    ep = h.entrypoint()
+    dead = dead[dead != ep]
+    for i in dead:
+        h.delete(int(i))
+    for i in dead:
+        g.delete(str(int(i)))
+    assert g.size() == h.size()
+    q = gaussian(100, 24, 8)
+    o_ids, _, o_cnt, _ = h.search_batch(q, 10, 64, nthreads=4)
+    ids, dist, cnt = g.search_batch(q, SearchParams(top_k=10, ef_search=64))
+    assert not np.isin(ids, dead).any()
+    assert np.array_equal(cnt, o_cnt) and recall(ids, o_ids) >= 0.99
+
+
+def test_empty_and_single_and_toy_graphs():
+    g = GPUHNSWIndex(HNSWParams(), DistanceMetric.L2, 3)
+    ids, dist, cnt = g.search_batch(np.zeros((2, 3), np.float32), SearchParams(top_k=5))  # hnsw_test.go:47-75
+    assert np.all(cnt == 0)
+    h = oracle.OracleHNSW(metric=1)
+    h.insert(1, [1.0, 2.0, 3.0])
+    g.import_graph_state(to_graph_state(h.export_graph_state(), 16))
+    res = g.search([1.1, 2.1, 3.1], SearchParams(top_k=1))                                  # hnsw_test.go:77-122
+    assert len(res) == 1 and res[0].vector.id == 1
+    h = oracle.OracleHNSW(metric=1)
+    h.build(np.array([[1, 0], [0, 1], [1, 1], [2, 2]], np.float32))
+    g2 = GPUHNSWIndex(HNSWParams(), DistanceMetric.L2, 2)
+    g2.import_graph_state(to_graph_state(h.export_graph_state(), 16))
+    res = g2.search([0.0, 0.0], SearchParams(top_k=2))                                      # hnsw_test.go:124-160
+    o = h.search([0.0, 0.0], 2)
+    assert [r.vector.id for r in res] == list(o[0]) and [np.float32(r.distance) for r in res] == list(o[1])
+    with pytest.raises(ScintireteError):
+        g2.build([])
+
+
+def test_visited_overflow_path_gives_same_answer():
+    # tiny M with a large ef forces far more visits per expansion budget than the shared-memory
+    # table is sized for -> exercises the global-memory overflow pass
+    db, h, g = _pair(DistanceMetric.L2, 5000, 8, M=48, efc=64)
+    q = gaussian(50, 8, 3)
+    o_ids, _, o_cnt, _ = h.search_batch(q, 10, 16, nthreads=4)
+    ids, _, cnt = g.search_batch(q, SearchParams(top_k=10, ef_search=16))
+    assert np.array_equal(cnt, o_cnt) and recall(ids, o_ids) >= 0.99
