@@ -168,8 +168,13 @@ SCN_API int32_t scn_merge_topk_dev(int32_t device, const uint64_t* d_keys, const
  * rerank; "tensor_min_batch" (auto crossover); "overfetch" (candidates kept per query and column
  * block by the tensor filter); "profile" 1 = record per-kernel CUDA-event timings. */
 SCN_API int32_t scn_set_option(scn_store* s, const char* name, int64_t value);
-/* Per-kernel timings of the last profiled search on this store: names[i] -> ms[i]; returns count. */
-SCN_API int32_t scn_last_timings(scn_store* s, const char** names, float* ms, int32_t max_entries);
+/* Per-kernel CUDA-event timings accumulated since the previous call (option "profile" = 1):
+ * names[i] -> total ms[i] over counts[i] launches. Synchronises on the recorded events, then
+ * clears them. Returns the number of entries written. */
+SCN_API int32_t scn_last_timings(scn_store* s, const char** names, float* ms, uint32_t* counts, int32_t max_entries);
+/* Test hook: raw filter scores of the tensor-core path, out_scores[nq][rows] (host), where
+ * score = aux[row] + c * (bf16(q) . mirror[row]) with c = -2 (L2) or -1 (inner product, cosine). */
+SCN_API int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t nq, float* out_scores);
 /* Counters of the last flat search: [0] queries served by the tensor path, [1] queries whose
  * certificate failed and were re-scanned exactly, [2] candidates reranked. */
 SCN_API int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n);

@@ -53,8 +53,9 @@ SIGNATURES = {
     "scn_merge_topk_dev": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scn_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
-    "scn_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), f32p, C.c_int32]),
+    "scn_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), f32p, u32p, C.c_int32]),
     "scn_last_counters": (C.c_int32, [C.c_void_p, u64p, C.c_int32]),
+    "scn_debug_tensor_scores": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
 }
 
 _lib = None

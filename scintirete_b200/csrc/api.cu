@@ -31,12 +31,7 @@ static int32_t flat_keys(scn_store* s, const float* d_q, uint64_t nq, uint32_t k
     tensor = tensor_path_supported(s, k) && (int64_t)nq >= s->opt_tensor_min_batch && s->rows >= 4096;
   }
   if (tensor) return flat_search_tensor(s, d_q, nq, k, row_base, d_keys, stream, prof);
-  {
-    std::lock_guard<std::mutex> lk(s->mu);
-    s->counters[0] = 0;
-    s->counters[1] = 0;
-    s->counters[2] = 0;
-  }
+  SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
   return flat_search_exact(s, d_q, nullptr, nullptr, nq, k, row_base, d_keys, stream, prof);
 }
 
@@ -171,7 +166,7 @@ int32_t scn_rerank(scn_store* s, const float* q, uint64_t nq, const uint64_t* ca
   SCN_TRY(scratch.alloc(&d_counts, nq));
   SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
   SCN_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  SCN_TRY(rerank_rows(s, d_q, nq, d_rows, ncand, k, d_keys, st));
+  SCN_TRY(rerank_rows(s, d_q, nq, d_rows, ncand, k, 0, d_keys, st));
   SCN_TRY(keys_to_results(s, d_keys, nq, 0, d_ids, d_dist, d_counts, k, st));
   SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -198,6 +193,22 @@ int32_t scn_distance_batch(int32_t device, int32_t metric, const float* q, uint6
   SCN_CUDA(cudaMemcpyAsync(d_x, x, nx * dim * sizeof(float), cudaMemcpyHostToDevice, st));
   SCN_TRY(distance_batch(metric, d_q, nq, d_x, nx, dim, d_o, st));
   SCN_CUDA(cudaMemcpyAsync(out, d_o, nq * nx * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  return SCN_OK;
+}
+
+int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t nq, float* out_scores) {
+  if (!s || !q || !out_scores) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  if (!tensor_path_supported(s, 10)) return fail(SCN_ERR_INVALID_PARAMETERS, "tensor-core path unsupported for dim=%u", s->dim);
+  DeviceGuard g(s->device);
+  cudaStream_t st = thread_stream(s->device);
+  Scratch scratch(st);
+  float *d_q = nullptr, *d_o = nullptr;
+  SCN_TRY(scratch.alloc(&d_q, nq * s->dim));
+  SCN_TRY(scratch.alloc(&d_o, nq * s->rows));
+  SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCN_TRY(tensor_debug_scores(s, d_q, nq, d_o, st));
+  SCN_CUDA(cudaMemcpyAsync(out_scores, d_o, nq * s->rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaStreamSynchronize(st));
   return SCN_OK;
 }

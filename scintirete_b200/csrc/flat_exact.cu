@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ v
 }
 
 int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand, uint32_t k,
-                    uint64_t* d_out_keys, cudaStream_t stream) {
+                    uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream) {
   if (nq == 0) return SCN_OK;
   uint32_t ncand_pad = std::max(32u, next_pow2(ncand));
   size_t smem = (size_t)s->pitch * 4 + (size_t)ncand_pad * 8;
@@ -412,8 +412,8 @@ int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t*
   do {                                                                                                            \
     SCN_CUDA(cudaFuncSetAttribute(rerank_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     rerank_kernel<MT><<<(unsigned)nq, 128, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,   \
-                                                           (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k, 0, \
-                                                           d_out_keys);                                           \
+                                                           (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k,      \
+                                                           (uint32_t)row_base, d_out_keys);                       \
   } while (0)
   switch (s->metric) {
     case M_L2: RR(M_L2); break;

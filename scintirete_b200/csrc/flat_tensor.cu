@@ -1,12 +1,662 @@
-// flat_tensor.cu — K2: tensor-core (tcgen05) candidate filter for large query batches.
+// flat_tensor.cu — K2: tensor-core candidate filter for large query batches, plus the certified
+// exact rerank that makes its results identical to the exact scan.
+//
+// Pipeline (all asynchronous on one stream):
+//   prep_queries      q -> bf16 q~ (tensor operand), ||q||, ||q~||, ||q - q~||
+//   tensor_filter     tcgen05 GEMM  S = aux[x] + c * (q~ . x~)   (c = -2 for L2, -1 for IP/cosine),
+//                     128 queries stationary in TMEM (A operand), bf16 mirror rows streamed by TMA
+//                     (B operand, 128B-swizzled K-major tiles), fp32 accumulators in TMEM (double
+//                     buffered); the epilogue warps read the accumulators with tcgen05.ld and keep,
+//                     per query, the k' best (score,row) of their column chunk — the score matrix
+//                     is never materialised.
+//   merge_candidates  per query: union of the chunk lists -> best k'' rows + tau (a lower bound on
+//                     the filter score of every row NOT passed on)
+//   rerank_rows       exact reference arithmetic on the k'' rows -> exact top-k keys
+//   certify           proves from tau and rigorous rounding bounds that no other row can enter the
+//                     top-k (ties included); queries that cannot be certified are appended to a list
+//   flat_search_exact exact scan for the listed queries (normally none)
+//
+// Roofline of tensor_filter: tensor pipe, 2*nq*N*D flop; HBM side reads the bf16 mirror once per
+// wave of query blocks (L2 keeps the tile window shared by the CTAs that walk the same chunk).
+#include <cuda.h>
+
 #include "store.h"
 
 namespace scn {
 
-bool tensor_path_supported(const scn_store*, uint32_t) { return false; }
+constexpr int TF_BM = 128;        // queries per CTA (UMMA M)
+constexpr int TF_BK = 64;         // bf16 per smem K block = one 128-byte swizzle row
+constexpr int TF_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (TMEM lane quarters 2,3,0,1)
+constexpr int TF_MAX_KPAD = 768;  // A operand must fit TMEM next to the accumulators
 
-int32_t flat_search_tensor(scn_store*, const float*, uint64_t, uint32_t, uint64_t, uint64_t*, cudaStream_t, Profiler*) {
-  return fail(SCN_ERR_INTERNAL, "tensor-core flat path not built");
+// ---- PTX helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (bf16 in, fp32 accumulate), M=128
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float v[32]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// 128B-swizzled K-major smem operand descriptor (rows of 128 B, 8-row atoms of 1024 B)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row atom
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+struct FilterArgs {
+  const __nv_bfloat16* qb;  // [n_qblocks*128][kpad]
+  const float* aux;         // [n_rows]
+  uint32_t nq, n_rows, kpad;
+  uint32_t n_qblocks, n_chunks, tiles_per_chunk, n_tiles;
+  uint32_t kprime;
+  float coef;               // -2 (L2) or -1 (IP, cosine)
+  float* cand_score;        // [nq][n_chunks][kprime]
+  uint32_t* cand_row;       // [nq][n_chunks][kprime]
+  float* chunk_tau;         // [nq][n_chunks]
+  float* dbg_scores;        // optional [nq][n_rows]
+};
+
+template <int BN>
+struct FilterCfg {
+  static constexpr int STAGE_BYTES = BN * TF_BK * 2;
+  static constexpr int STAGES = (BN == 64) ? 16 : 8;
+  static constexpr int ACC_COLS = 2 * BN;  // two accumulator buffers
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
+  using Cfg = FilterCfg<BN>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve-up: [B stages][cand_score 128*kprime][cand_row 128*kprime][aux 2*BN][barriers][tmem ptr]
+  unsigned char* sb = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_cscore = reinterpret_cast<float*>(sb + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint32_t* s_crow = reinterpret_cast<uint32_t*>(s_cscore + 128 * a.kprime);
+  float* s_aux = reinterpret_cast<float*>(s_crow + 128 * a.kprime);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 2 * BN);
+  uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
+  uint64_t* empty = full + Cfg::STAGES;         // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = empty + Cfg::STAGES;     // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;           // [2]       epilogue -> MMA
+  uint64_t* a_ready = acc_empty + 2;            // [1]       epilogue (A stored) -> MMA
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t KB = a.kpad / TF_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, 4);  // one arrive per epilogue warp
+    }
+    mbar_init(a_ready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // TMEM: all 512 columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_acc = tmem_base;                   // columns [0, 2*BN)
+  const uint32_t tmem_a = tmem_base + Cfg::ACC_COLS;     // columns [2*BN, 2*BN + kpad/2)
+
+  const uint32_t n_items = a.n_qblocks * a.n_chunks;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t chunk = item / a.n_qblocks;
+        const uint32_t t0 = chunk * a.tiles_per_chunk;
+        const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+        for (uint32_t t = t0; t < t1; ++t) {
+          for (uint32_t kb = 0; kb < KB; ++kb) {
+            mbar_wait(empty + stage, phase ^ 1);
+            mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
+            tma_load_2d(sb + stage * Cfg::STAGE_BYTES, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * BN));
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, acc_it = 0, a_phase = 0;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t chunk = item / a.n_qblocks;
+        const uint32_t t0 = chunk * a.tiles_per_chunk;
+        const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+        mbar_wait(a_ready, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
+          const uint32_t buf = acc_it & 1;
+          mbar_wait(acc_empty + buf, ((acc_it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_acc + buf * BN;
+          for (uint32_t kb = 0; kb < KB; ++kb) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            const uint64_t bdesc = make_b_desc(smem_u32(sb + stage * Cfg::STAGE_BYTES));
+#pragma unroll
+            for (uint32_t k = 0; k < TF_BK / 16; ++k) {
+              // A: 16 bf16 of K = 8 TMEM columns; B: 32 bytes further along the swizzled row
+              tc_mma_ts(d_tmem, tmem_a + kb * (TF_BK / 2) + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            tc_commit(empty + stage);  // smem slot free once these MMAs retire
+            if (++stage == Cfg::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          tc_commit(acc_full + buf);  // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps: thread <-> query (TMEM lane) =====
+    const uint32_t quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const uint32_t qrow = quarter * 32 + lane;         // query row within the block == TMEM lane
+    const uint32_t et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
+    const uint32_t lane_addr = (quarter * 32) << 16;
+    const uint32_t kp = a.kprime;
+    float* my_score = s_cscore + qrow;                 // slot j at [j*128]
+    uint32_t* my_row = s_crow + qrow;
+    uint32_t acc_it = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint32_t chunk = item / a.n_qblocks;
+      const uint32_t qblk = item - chunk * a.n_qblocks;
+      const uint32_t t0 = chunk * a.tiles_per_chunk;
+      const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+      const uint32_t q_global = qblk * TF_BM + qrow;
+      // ---- A operand: this thread's query row -> its TMEM lane, packed bf16 pairs ----
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)q_global * a.kpad);
+        const uint32_t n16 = a.kpad / 8;  // 16-byte groups = 4 TMEM columns each
+        for (uint32_t i = 0; i < n16; ++i) {
+          uint4 v = __ldg(src + i);
+          tc_st4(tmem_a + lane_addr + i * 4, v.x, v.y, v.z, v.w);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+      }
+      for (uint32_t j = 0; j < kp; ++j) {
+        my_score[j * 128] = __int_as_float(0x7f800000);
+        my_row[j * 128] = ROW_NONE;
+      }
+      float theta = __int_as_float(0x7f800000);  // current k'-th best score of this query in this chunk
+      for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
+        const uint32_t buf = acc_it & 1;
+        const uint32_t col0 = t * BN;
+        // stage the per-column additive term (||x~||^2, 0, or +Inf for deleted / out-of-range rows)
+        if (et < BN) {
+          uint32_t c = col0 + et;
+          s_aux[buf * BN + et] = (c < a.n_rows) ? __ldg(a.aux + c) : __int_as_float(0x7f800000);
+        }
+        epi_bar_sync();
+        mbar_wait(acc_full + buf, (acc_it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < BN / 32; ++g) {
+          float v[32];
+          tc_ld32(tmem_acc + lane_addr + buf * BN + g * 32, v);
+          tc_wait_ld();
+          const float4* ax = reinterpret_cast<const float4*>(s_aux + buf * BN + g * 32);
+          float best = __int_as_float(0x7f800000);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = ax[j];
+            v[4 * j + 0] = fmaf(a.coef, v[4 * j + 0], x.x);
+            v[4 * j + 1] = fmaf(a.coef, v[4 * j + 1], x.y);
+            v[4 * j + 2] = fmaf(a.coef, v[4 * j + 2], x.z);
+            v[4 * j + 3] = fmaf(a.coef, v[4 * j + 3], x.w);
+            best = fminf(best, fminf(fminf(v[4 * j + 0], v[4 * j + 1]), fminf(v[4 * j + 2], v[4 * j + 3])));
+          }
+          if (a.dbg_scores && q_global < a.nq) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t c = col0 + g * 32 + j;
+              if (c < a.n_rows) a.dbg_scores[(size_t)q_global * a.n_rows + c] = v[j];
+            }
+          }
+          if (best < theta) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = v[j];
+              if (s < theta) {
+                // sorted insertion; equal scores keep the earlier (lower) row first
+                uint32_t p = kp - 1;
+                while (p > 0 && my_score[(p - 1) * 128] > s) {
+                  my_score[p * 128] = my_score[(p - 1) * 128];
+                  my_row[p * 128] = my_row[(p - 1) * 128];
+                  --p;
+                }
+                my_score[p * 128] = s;
+                my_row[p * 128] = col0 + g * 32 + j;
+                theta = my_score[(kp - 1) * 128];
+              }
+            }
+          }
+        }
+        // accumulator buffer drained
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+      }
+      // ---- chunk result ----
+      if (q_global < a.nq) {
+        size_t base = ((size_t)q_global * a.n_chunks + chunk) * kp;
+        for (uint32_t j = 0; j < kp; ++j) {
+          a.cand_score[base + j] = my_score[j * 128];
+          a.cand_row[base + j] = my_row[j * 128];
+        }
+        a.chunk_tau[(size_t)q_global * a.n_chunks + chunk] = theta;
+      }
+      // all MMAs of this item have retired (the last acc_full was waited on), so A may be rewritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- query preparation ---------------------------------------------------------------------------
+// One warp per query: bf16 row (zero padded to kpad), and the norms the certificate needs.
+// qstat[q] = {||q||, ||q~||, ||q - q~||, ||q~||^2}
+__global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
+                                                           uint32_t kpad, __nv_bfloat16* __restrict__ qb,
+                                                           float4* __restrict__ qstat) {
+  uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= nq_pad) return;
+  float nn = 0.f, mm = 0.f, ee = 0.f;
+  for (uint32_t i = lane; i < kpad; i += 32) {
+    float v = (qi < nq && i < dim) ? q[(size_t)qi * dim + i] : 0.0f;
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    float bv = __bfloat162float(b);
+    qb[(size_t)qi * kpad + i] = b;
+    nn = fmaf(v, v, nn);
+    mm = fmaf(bv, bv, mm);
+    ee = fmaf(v - bv, v - bv, ee);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    mm += __shfl_xor_sync(0xffffffffu, mm, o);
+    ee += __shfl_xor_sync(0xffffffffu, ee, o);
+  }
+  if (lane == 0 && qi < nq) qstat[qi] = make_float4(sqrtf(nn), sqrtf(mm), sqrtf(ee), mm);
+}
+
+// ---- candidate merge: chunk lists -> k'' rows + tau -------------------------------------------------
+__global__ void __launch_bounds__(128) merge_candidates_kernel(const float* __restrict__ cand_score,
+                                                               const uint32_t* __restrict__ cand_row,
+                                                               const float* __restrict__ chunk_tau, uint32_t n_chunks,
+                                                               uint32_t kprime, uint32_t n_pad, uint32_t kpp,
+                                                               uint32_t* __restrict__ out_rows, float* __restrict__ out_tau) {
+  extern __shared__ __align__(16) unsigned char smem_merge[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_merge);  // [n_pad]
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = n_chunks * kprime;
+  for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    uint64_t key = KEY_NONE;
+    if (i < n) {
+      uint32_t row = cand_row[(size_t)q * n + i];
+      if (row != ROW_NONE) key = make_key(cand_score[(size_t)q * n + i], row);
+    }
+    keys[i] = key;
+  }
+  // block bitonic sort (ascending)
+  for (uint32_t size = 2; size <= n_pad; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (uint32_t t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+        uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        uint64_t x = keys[lo], y = keys[hi];
+        if ((x > y) == up) {
+          keys[lo] = y;
+          keys[hi] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kpp; i += blockDim.x) {
+    uint64_t key = (i < n_pad) ? keys[i] : KEY_NONE;
+    out_rows[(size_t)q * kpp + i] = (key == KEY_NONE) ? ROW_NONE : (uint32_t)key;
+  }
+  if (threadIdx.x == 0) {
+    // tau = lower bound on the filter score of every row that is not handed to the rerank:
+    // rows never kept by a chunk (>= that chunk's tau) and rows dropped here (>= keys[kpp])
+    float tau = __int_as_float(0x7f800000);
+    for (uint32_t c = 0; c < n_chunks; ++c) tau = fminf(tau, chunk_tau[(size_t)q * n_chunks + c]);
+    if (kpp < n_pad && keys[kpp] != KEY_NONE) tau = fminf(tau, ord_f32((uint32_t)(keys[kpp] >> 32)));
+    out_tau[q] = tau;
+  }
+}
+
+// ---- certificate -------------------------------------------------------------------------------------
+// For query q let d_k be the k-th exact distance found by the rerank. Every row x that was not
+// reranked has filter score s~(x) >= tau. With
+//   E  = ||q - q~||*Mmax + ||q||*Emax + e_tc     (bf16 rounding of both operands; Mmax = max ||mirror row||,
+//                                                 Emax = max ||row - mirror row||; e_tc = fp32 accumulation
+//                                                 error of the tensor pipe, bounded by 8*K*2^-24*||q~||*Mmax)
+//   g  = 1.01*(D+2)*2^-24                        (the reference's own sequential fp32 summation error)
+// the reference distance of such a row is bounded below by LB (per metric, see below). The query is
+// certified iff LB > d_k strictly, so neither a closer row nor a tie with a lower row index can have
+// been missed. Anything else goes to the exact scan.
+__global__ void certify_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ tau, const float4* __restrict__ qstat,
+                               const float* __restrict__ bounds, uint32_t nq, uint32_t k, uint32_t dim, uint32_t kpad,
+                               int metric, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count,
+                               unsigned long long* __restrict__ counters) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float INF = __int_as_float(0x7f800000);
+  uint64_t kk = keys[(size_t)q * k + (k - 1)];
+  float dk = (kk == KEY_NONE) ? INF : ord_f32((uint32_t)(kk >> 32));
+  float t = tau[q];
+  bool ok;
+  if (t == INF) {
+    ok = true;  // nothing was left out: the rerank saw every live row
+  } else if (!(dk < INF)) {
+    ok = false;  // fewer than k finite results although rows were left out
+  } else {
+    float4 st = qstat[q];
+    const float qn = st.x, qtn = st.y, eq = st.z, qtn2 = st.w;
+    const float Mmax = bounds[0], Emax = bounds[1], Xmax = bounds[2];
+    const float u = 5.9604645e-8f;  // 2^-24
+    const float etc = 8.0f * (float)kpad * u * qtn * Mmax;
+    const float E = (eq * Mmax + qn * Emax + etc) * 1.0001f;
+    const float g = 1.01f * (float)(dim + 2) * u;
+    float lb;
+    if (metric == M_IP) {
+      // d_ref(x) = -fl(q.x) >= -(q.x) - g*||q||*||x|| ;  -(q.x) >= s~ - E >= tau - E
+      lb = t - E - g * qn * Xmax;
+      lb -= fabsf(lb) * 4.0f * u;
+    } else if (metric == M_COS) {
+      // mirror rows are x/||x|| (fp32 divide, rel. error <= 2^-23 per element): -(q.x^) >= tau - E - ||q||*2^-22
+      // cos(x) = (q.x^)/||q|| <= (E' - tau)/||q||;  d_ref >= 1 - cos - (2g + 2^-21)
+      float Ep = E + qn * 4.0f * u;
+      float c = (Ep - t) / qn;
+      lb = 1.0f - c - (2.0f * g + 8.0f * u);
+      lb -= fabsf(lb) * 4.0f * u + 4.0f * u;
+      if (!(qn > 0.0f)) lb = -INF;  // zero query: every distance is exactly 1 -> ties everywhere
+    } else {
+      // ||q - x|| >= ||q~ - x~|| - ||q - q~|| - ||x - x~||, and ||q~ - x~||^2 = ||q~||^2 + s~ (s~ = ||x~||^2 - 2 q~.x~)
+      // fp32 error of s~: 2*e_tc plus the rounding of aux and of ||q~||^2 (<= K*2^-23 relative each)
+      float es = 2.0f * etc + (float)kpad * 2.0f * u * (Mmax * Mmax + qtn2);
+      float r2 = qtn2 + t - es;
+      float r = r2 > 0.0f ? sqrtf(r2) * (1.0f - 2.0f * u) : 0.0f;
+      lb = r - eq * 1.0001f - Emax;
+      lb = lb * (1.0f - g) * (1.0f - 4.0f * u);
+    }
+    ok = lb > dk;
+  }
+  if (!ok) {
+    uint32_t slot = atomicAdd(fail_count, 1u);
+    fail_list[slot] = q;
+  }
+  if (counters) {
+    atomicAdd(counters + 0, 1ull);
+    if (!ok) atomicAdd(counters + 1, 1ull);
+  }
+}
+
+__global__ void set_aux_kernel(float* aux, const uint32_t* rows, uint32_t n, float value) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) aux[rows[i]] = value;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool tensor_path_supported(const scn_store* s, uint32_t k) { return s->kpad <= TF_MAX_KPAD && k <= 64 && s->rows >= 1; }
+
+static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
+  uint32_t cmax = std::max(1u, std::min(256u, n_tiles / 8));
+  double best_eff = 0;
+  for (uint32_t c = 1; c <= cmax; ++c) {
+    uint32_t items = n_qb * c;
+    double eff = (double)items / ((double)((items + sms - 1) / sms) * sms);
+    best_eff = std::max(best_eff, eff);
+  }
+  for (uint32_t c = 1; c <= cmax; ++c) {
+    uint32_t items = n_qb * c;
+    double eff = (double)items / ((double)((items + sms - 1) / sms) * sms);
+    if (eff >= best_eff - 0.02) return c;
+  }
+  return 1;
+}
+
+template <int BN>
+static int32_t launch_filter(const CUtensorMap& tmap, const FilterArgs& fa, int grid, cudaStream_t stream) {
+  using Cfg = FilterCfg<BN>;
+  size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * fa.kprime * 8 + (size_t)2 * BN * 4 +
+                (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
+  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tensor_filter_kernel<BN><<<grid, TF_THREADS, smem, stream>>>(tmap, fa);
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
+static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
+                                        uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof, float* dbg_scores) {
+  int sms = 0;
+  SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
+  const uint32_t BN = (s->kpad > 512) ? 64 : 128;
+  const uint32_t n_rows = (uint32_t)s->rows;
+  const uint32_t n_tiles = (n_rows + BN - 1) / BN;
+  const uint32_t n_qb = (uint32_t)((nq + TF_BM - 1) / TF_BM);
+  const uint32_t nq_pad = n_qb * TF_BM;
+  uint32_t n_chunks = pick_chunks(n_qb, n_tiles, (uint32_t)sms);
+  uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
+  n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+  uint32_t kprime = s->opt_overfetch > 0 ? (uint32_t)s->opt_overfetch : std::max(16u, round_up(k + k / 2 + 1, 8));
+  kprime = std::min(kprime, 96u);
+  if (kprime < k) return fail(SCN_ERR_INVALID_PARAMETERS, "overfetch %u is below k=%u", kprime, k);
+  const uint32_t n_cand = n_chunks * kprime;
+  const uint32_t n_pad = std::max(32u, next_pow2(n_cand));
+  const uint32_t kpp = std::min(n_pad, std::max(32u, next_pow2(2 * k)));  // rows handed to the exact rerank
+
+  // B operand tensor map: mirror [rows][kpad] bf16, box {64, BN}, 128B swizzle, OOB rows read as zero
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {s->kpad, n_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)s->kpad * 2};
+  cuuint32_t box[2] = {TF_BK, BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s->d_mirror, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  Scratch scratch(stream);
+  __nv_bfloat16* d_qb = nullptr;
+  float4* d_qstat = nullptr;
+  float *d_cscore = nullptr, *d_ctau = nullptr, *d_tau = nullptr;
+  uint32_t *d_crow = nullptr, *d_rows = nullptr, *d_fail = nullptr, *d_nfail = nullptr;
+  SCN_TRY(scratch.alloc(&d_qb, (size_t)nq_pad * s->kpad));
+  SCN_TRY(scratch.alloc(&d_qstat, nq));
+  SCN_TRY(scratch.alloc(&d_cscore, (size_t)nq * n_cand));
+  SCN_TRY(scratch.alloc(&d_crow, (size_t)nq * n_cand));
+  SCN_TRY(scratch.alloc(&d_ctau, (size_t)nq * n_chunks));
+  SCN_TRY(scratch.alloc(&d_tau, nq));
+  SCN_TRY(scratch.alloc(&d_rows, (size_t)nq * kpp));
+  SCN_TRY(scratch.alloc(&d_fail, nq));
+  SCN_TRY(scratch.alloc(&d_nfail, 1));
+  SCN_CUDA(cudaMemsetAsync(d_nfail, 0, sizeof(uint32_t), stream));
+
+  if (prof) prof->begin("prep_queries");
+  prep_queries_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(d_q, (uint32_t)nq, nq_pad, s->dim, s->kpad, d_qb, d_qstat);
+  SCN_LAUNCHED();
+  if (prof) prof->end();
+
+  FilterArgs fa;
+  fa.qb = d_qb;
+  fa.aux = s->d_aux;
+  fa.nq = (uint32_t)nq;
+  fa.n_rows = n_rows;
+  fa.kpad = s->kpad;
+  fa.n_qblocks = n_qb;
+  fa.n_chunks = n_chunks;
+  fa.tiles_per_chunk = tiles_per_chunk;
+  fa.n_tiles = n_tiles;
+  fa.kprime = kprime;
+  fa.coef = (s->metric == M_L2) ? -2.0f : -1.0f;
+  fa.cand_score = d_cscore;
+  fa.cand_row = d_crow;
+  fa.chunk_tau = d_ctau;
+  fa.dbg_scores = dbg_scores;
+  int grid = (int)std::min<uint32_t>((uint32_t)sms, n_qb * n_chunks);
+  if (prof) prof->begin("tensor_filter");
+  int32_t rc = (BN == 64) ? launch_filter<64>(tmap, fa, grid, stream) : launch_filter<128>(tmap, fa, grid, stream);
+  if (prof) prof->end();
+  SCN_TRY(rc);
+
+  if (prof) prof->begin("merge_candidates");
+  merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_chunks, kprime, n_pad, kpp,
+                                                                            d_rows, d_tau);
+  SCN_LAUNCHED();
+  if (prof) prof->end();
+
+  if (prof) prof->begin("rerank_exact");
+  SCN_TRY(rerank_rows(s, d_q, nq, d_rows, kpp, k, row_base, d_out_keys, stream));
+  if (prof) prof->end();
+
+  if (prof) prof->begin("certify");
+  certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau, d_qstat, s->d_bounds, (uint32_t)nq, k, s->dim,
+                                                                   s->kpad, s->metric, d_fail, d_nfail, s->d_counters);
+  SCN_LAUNCHED();
+  if (prof) prof->end();
+
+  // exact scan for whatever could not be certified (normally nothing: the kernel exits at once)
+  return flat_search_exact(s, d_q, d_fail, d_nfail, nq, k, row_base, d_out_keys, stream, prof);
+}
+
+int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys,
+                           cudaStream_t stream, Profiler* prof) {
+  SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+  // bound the scratch of the (normally idle) exact fallback: sms * nq * k * 8 bytes of partial lists
+  const uint64_t max_batch = std::max<uint64_t>(1024, (512ull << 20) / ((uint64_t)160 * k * 8));
+  for (uint64_t q0 = 0; q0 < nq; q0 += max_batch) {
+    uint64_t n = std::min(max_batch, nq - q0);
+    SCN_TRY(flat_search_tensor_batch(s, d_q + q0 * s->dim, n, k, row_base, d_out_keys + q0 * k, stream, prof, nullptr));
+  }
+  return SCN_OK;
+}
+
+int32_t tensor_debug_scores(scn_store* s, const float* d_q, uint64_t nq, float* d_scores, cudaStream_t stream) {
+  Scratch scratch(stream);
+  uint64_t* d_keys = nullptr;
+  SCN_TRY(scratch.alloc(&d_keys, nq * 10));
+  return flat_search_tensor_batch(s, d_q, nq, 10, 0, d_keys, stream, nullptr, d_scores);
+}
+
+int32_t mark_aux_deleted(scn_store* s, const uint32_t* h_rows, uint32_t n, cudaStream_t stream) {
+  if (!n) return SCN_OK;
+  Scratch scratch(stream);
+  uint32_t* d_rows = nullptr;
+  SCN_TRY(scratch.alloc(&d_rows, n));
+  SCN_CUDA(cudaMemcpyAsync(d_rows, h_rows, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  set_aux_kernel<<<(n + 127) / 128, 128, 0, stream>>>(s->d_aux, d_rows, n, INFINITY);
+  SCN_LAUNCHED();
+  SCN_CUDA(cudaStreamSynchronize(stream));
+  return SCN_OK;
 }
 
 }  // namespace scn

@@ -453,13 +453,8 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.out_ids = d_out_ids;
   a.out_dist = d_out_dist;
   a.out_counts = d_out_counts;
-  a.stats = nullptr;
-  unsigned long long* d_stats = nullptr;
-  if (s->opt_profile) {
-    SCN_TRY(scratch.alloc(&d_stats, 2));
-    SCN_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), stream));
-    a.stats = d_stats;
-  }
+  SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+  a.stats = s->opt_profile ? s->d_counters : nullptr;
   // shrink the table until at least one block fits
   while ((((size_t)a.pitch * 4 + (size_t)a.ef_pad * 12 + (size_t)a.hash_size * 4) * HNSW_WARPS) > 200 * 1024 &&
          a.hash_size > 1024)
@@ -471,14 +466,6 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
     default: rc = launch_hnsw<M_IP>(a, sms, stream, scratch, prof); break;
   }
   SCN_TRY(rc);
-  if (d_stats) {
-    unsigned long long h[2];
-    SCN_CUDA(cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
-    SCN_CUDA(cudaStreamSynchronize(stream));
-    std::lock_guard<std::mutex> lk(s->mu);
-    s->counters[0] = h[0];
-    s->counters[1] = h[1];
-  }
   return SCN_OK;
 }
 

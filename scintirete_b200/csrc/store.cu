@@ -42,20 +42,13 @@ cudaStream_t thread_stream(int device) {
 
 void Profiler::collect() {
   if (!on || ev.empty()) return;
-  cudaEventSynchronize(ev.back().second.second);
   std::lock_guard<std::mutex> lk(s->mu);
-  s->timing_names.clear();
-  s->timing_ms.clear();
-  for (auto& e : ev) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
-    s->timing_names.push_back(e.first);
-    s->timing_ms.push_back(ms);
-  }
+  for (auto& e : ev) s->pending.push_back({e.first, e.second.first, e.second.second});
+  ev.clear();
 }
 
 Profiler::~Profiler() {
-  for (auto& e : ev) {
+  for (auto& e : ev) {  // only reached when collect() was not called (error paths)
     cudaEventDestroy(e.second.first);
     cudaEventDestroy(e.second.second);
   }
@@ -211,6 +204,12 @@ int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store
     return cuda_fail(cudaGetLastError(), "cudaMalloc(bounds)", __FILE__, __LINE__);
   }
   cudaMemset(s->d_bounds, 0, 4 * sizeof(float));
+  if (cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    cudaFree(s->d_bounds);
+    delete s;
+    return cuda_fail(cudaGetLastError(), "cudaMalloc(counters)", __FILE__, __LINE__);
+  }
+  cudaMemset(s->d_counters, 0, 4 * sizeof(unsigned long long));
   *out = s;
   return SCN_OK;
 }
@@ -219,6 +218,10 @@ int32_t scn_store_destroy(scn_store* s) {
   if (!s) return SCN_OK;
   DeviceGuard g(s->device);
   cudaDeviceSynchronize();
+  for (auto& e : s->pending) {
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
   free_graph(s);
   cudaFree(s->d_vec);
   cudaFree(s->d_norm);
@@ -227,6 +230,7 @@ int32_t scn_store_destroy(scn_store* s) {
   cudaFree(s->d_ids);
   cudaFree(s->d_deleted);
   cudaFree(s->d_bounds);
+  cudaFree(s->d_counters);
   delete s;
   return SCN_OK;
 }
@@ -349,7 +353,8 @@ int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
   }
   SCN_CUDA(cudaMemcpyAsync(s->d_deleted, bits.data(), words * 4, cudaMemcpyHostToDevice, st));
   SCN_CUDA(cudaStreamSynchronize(st));
-  return SCN_OK;
+  // the tensor filter learns about deletions through its per-row additive term (+Inf)
+  return mark_aux_deleted(s, rows.data(), (uint32_t)rows.size(), st);
 }
 
 int32_t scn_store_stats(scn_store* s, scn_stats* out) {
@@ -475,22 +480,51 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
   return SCN_OK;
 }
 
-int32_t scn_last_timings(scn_store* s, const char** names, float* ms, int32_t max_entries) {
+int32_t scn_last_timings(scn_store* s, const char** names, float* ms, uint32_t* counts, int32_t max_entries) {
   if (!s) return 0;
+  DeviceGuard g(s->device);
   std::lock_guard<std::mutex> lk(s->mu);
-  int32_t n = (int32_t)std::min<size_t>(s->timing_names.size(), (size_t)std::max(0, max_entries));
+  static thread_local std::vector<std::string> name_store;
+  name_store.clear();
+  std::vector<float> total;
+  std::vector<uint32_t> cnt;
+  for (auto& e : s->pending) {
+    cudaEventSynchronize(e.b);
+    float t = 0;
+    cudaEventElapsedTime(&t, e.a, e.b);
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+    size_t i = 0;
+    for (; i < name_store.size(); ++i)
+      if (name_store[i] == e.name) break;
+    if (i == name_store.size()) {
+      name_store.push_back(e.name);
+      total.push_back(0.f);
+      cnt.push_back(0);
+    }
+    total[i] += t;
+    cnt[i] += 1;
+  }
+  s->pending.clear();
+  int32_t n = (int32_t)std::min<size_t>(name_store.size(), (size_t)std::max(0, max_entries));
   for (int32_t i = 0; i < n; ++i) {
-    if (names) names[i] = s->timing_names[i].c_str();
-    if (ms) ms[i] = s->timing_ms[i];
+    if (names) names[i] = name_store[i].c_str();
+    if (ms) ms[i] = total[i];
+    if (counts) counts[i] = cnt[i];
   }
   return n;
 }
 
 int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n) {
   if (!s || !out) return 0;
-  std::lock_guard<std::mutex> lk(s->mu);
+  DeviceGuard g(s->device);
+  unsigned long long h[4] = {0, 0, 0, 0};
+  if (cudaMemcpy(h, s->d_counters, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   int32_t m = std::min(n, 4);
-  for (int32_t i = 0; i < m; ++i) out[i] = s->counters[i];
+  for (int32_t i = 0; i < m; ++i) out[i] = h[i];
   return m;
 }
 

@@ -40,6 +40,9 @@ struct scn_store {
   // running maxima over rows, for the tensor-path certificate (device float[4]):
   //   [0] max ||mirror row||   [1] max ||x_true - mirror row||   [2] max ||x||   [3] reserved
   float* d_bounds = nullptr;
+  // device counters of the last search: flat: [0] queries through the tensor filter, [1] queries
+  // re-scanned exactly (certificate failed); hnsw: [0] distance evaluations, [1] expansions
+  unsigned long long* d_counters = nullptr;
 
   bool auto_ids = true;  // every id so far was row+1 -> no host map needed
   std::unordered_map<uint64_t, uint32_t> row_of;
@@ -61,11 +64,14 @@ struct scn_store {
   int64_t opt_overfetch = 0;  // 0 = auto
   int64_t opt_profile = 0;
 
-  // introspection (protected by mu)
+  // introspection (protected by mu). Profiled kernels leave (name, start, stop) event triples
+  // here; scn_last_timings synchronises on them, sums per name and clears the list.
   std::mutex mu;
-  std::vector<std::string> timing_names;
-  std::vector<float> timing_ms;
-  uint64_t counters[4] = {0, 0, 0, 0};
+  struct TimedEvent {
+    std::string name;
+    cudaEvent_t a, b;
+  };
+  std::vector<TimedEvent> pending;
 
   uint64_t device_bytes() const;
   bool lookup(uint64_t id, uint32_t* row) const {
@@ -138,7 +144,7 @@ struct Profiler {
     if (!on) return;
     cudaEventRecord(ev.back().second.second, stream);
   }
-  // requires the stream to be synchronised by the caller (or syncs on the last event)
+  // hands the recorded events to the store (no synchronisation here)
   void collect();
   ~Profiler();
 };
@@ -157,7 +163,9 @@ int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t
                            uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof);
 bool tensor_path_supported(const scn_store* s, uint32_t k);
 int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand,
-                    uint32_t k, uint64_t* d_out_keys, cudaStream_t stream);
+                    uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream);
+int32_t tensor_debug_scores(scn_store* s, const float* d_q, uint64_t nq, float* d_scores, cudaStream_t stream);
+int32_t mark_aux_deleted(scn_store* s, const uint32_t* h_rows, uint32_t n, cudaStream_t stream);
 int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                     float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, Profiler* prof);
 int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const float* d_x, uint64_t nx, uint32_t dim,

@@ -153,15 +153,13 @@ class DeviceStore:
     def set_option(self, name: str, value: int):
         _check(_native.lib().scn_set_option(self._h, name.encode(), value))
 
-    def last_timings(self) -> Dict[str, float]:
+    def last_timings(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel: (total ms, launches)} since the previous call (needs option profile=1)."""
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()
-        n = _native.lib().scn_last_timings(self._h, names, ms, 32)
-        out: Dict[str, float] = {}
-        for i in range(n):
-            key = names[i].decode()
-            out[key] = out.get(key, 0.0) + float(ms[i])
-        return out
+        cnt = (C.c_uint32 * 32)()
+        n = _native.lib().scn_last_timings(self._h, names, ms, cnt, 32)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
     def last_counters(self) -> List[int]:
         c = (C.c_uint64 * 4)()

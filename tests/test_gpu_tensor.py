@@ -1,0 +1,131 @@
+"""GPU parity of the tensor-core flat path (tcgen05 filter + certified exact rerank): the result
+must be IDENTICAL (ids and fp32 distance bits) to the CPU oracle, because every returned distance
+is recomputed in the reference's arithmetic and the certificate (or the exact re-scan behind it)
+guarantees that no row was missed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from scintirete_b200 import DeviceStore, DistanceMetric, _native
+from util import gaussian
+
+pytestmark = pytest.mark.gpu
+METRICS = [DistanceMetric.L2, DistanceMetric.COSINE, DistanceMetric.INNER_PRODUCT]
+
+
+def bf16_round(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def debug_scores(store, q):
+    q = np.ascontiguousarray(q, np.float32)
+    n = int(store.stats().rows)
+    out = np.empty((q.shape[0], n), np.float32)
+    rc = _native.lib().scn_debug_tensor_scores(store.handle, q.ctypes.data_as(C.c_void_p), q.shape[0],
+                                               out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, _native.last_error()
+    return out
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,d,nq", [(3000, 768, 130), (2500, 128, 70), (1000, 200, 5)])
+def test_filter_scores_match_bf16_emulation(metric, n, d, nq):
+    db, q = gaussian(n, d, 1), gaussian(nq, d, 2)
+    s = DeviceStore(d, metric)
+    s.append(db)
+    got = debug_scores(s, q)
+    s.close()
+    x = db.astype(np.float32)
+    if metric == DistanceMetric.COSINE:
+        x = x * (np.float32(1) / np.sqrt((x.astype(np.float64) ** 2).sum(1)).astype(np.float32))[:, None]
+    xb, qb = bf16_round(x).astype(np.float64), bf16_round(q).astype(np.float64)
+    dot = qb @ xb.T
+    want = (xb ** 2).sum(1)[None, :] - 2 * dot if metric == DistanceMetric.L2 else -dot
+    err = np.abs(got - want).max()
+    scale = np.abs(want).max()
+    assert err <= 2e-5 * scale + 2e-3, (err, scale)
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 300, 10), (6000, 128, 130, 10), (9999, 200, 77, 1), (5000, 64, 129, 32)])
+def test_tensor_path_bit_exact_vs_oracle(metric, n, d, nq, k):
+    db, q = gaussian(n, d, 1234), gaussian(nq, d, 4321)
+    s = DeviceStore(d, metric)
+    s.set_option("flat_path", 2)
+    s.append(db)
+    ids, dist, cnt = s.search_flat(q, k)
+    tensor_q, rescanned = s.last_counters()[:2]
+    s.close()
+    o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, nthreads=8)
+    assert np.array_equal(ids, o_ids)
+    assert np.array_equal(dist, o_dist)
+    assert np.array_equal(cnt, o_cnt)
+    assert tensor_q == nq
+    assert rescanned <= 0.02 * nq + 1, f"{rescanned} of {nq} queries failed the certificate on Gaussian data"
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_tensor_path_with_deleted_rows_and_ids(metric):
+    n, d, nq = 8000, 96, 140
+    db, q = gaussian(n, d, 5), gaussian(nq, d, 6)
+    ids_ext = np.arange(n, dtype=np.uint64) * 3 + 11
+    dele = np.zeros(n, np.uint8)
+    dele[::4] = 1
+    s = DeviceStore(d, metric)
+    s.set_option("flat_path", 2)
+    s.append(db, ids_ext)
+    s.mark_deleted(ids_ext[dele.astype(bool)])
+    ids, dist, cnt = s.search_flat(q, 10)
+    s.close()
+    o = oracle.flat_search(int(metric), db, q, 10, ids=ids_ext, deleted=dele, nthreads=8)
+    assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+
+
+def test_ties_force_exact_rescan_and_stay_exact():
+    # every row identical (the reference's own benchmark data, hnsw_test.go:473-479): the filter
+    # cannot separate anything, the certificate must refuse, the exact scan must answer
+    v = (np.arange(128, dtype=np.float32) / 128)
+    db = np.tile(v, (5000, 1))
+    q = np.tile(v, (130, 1)) + gaussian(130, 128, 3) * np.float32(1e-3)
+    for metric in METRICS:
+        s = DeviceStore(128, metric)
+        s.set_option("flat_path", 2)
+        s.append(db)
+        ids, dist, cnt = s.search_flat(q, 10)
+        rescanned = s.last_counters()[1]
+        s.close()
+        o = oracle.flat_search(int(metric), db, q, 10, nthreads=8)
+        assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+        assert rescanned == 130
+
+
+def test_near_duplicates_cluster():
+    # tight clusters: many rows within bf16 noise of each other -> some queries need the re-scan,
+    # all must still be exact
+    rng = np.random.default_rng(9)
+    centers = rng.standard_normal((50, 256)).astype(np.float32)
+    db = (centers[rng.integers(0, 50, 6000)] + rng.standard_normal((6000, 256)).astype(np.float32) * np.float32(1e-3))
+    q = centers[rng.integers(0, 50, 150)] + rng.standard_normal((150, 256)).astype(np.float32) * np.float32(1e-3)
+    for metric in METRICS:
+        s = DeviceStore(256, metric)
+        s.set_option("flat_path", 2)
+        s.append(db)
+        ids, dist, _ = s.search_flat(q, 10)
+        s.close()
+        o = oracle.flat_search(int(metric), db, q, 10, nthreads=8)
+        assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+
+
+def test_auto_dispatch_uses_tensor_path_for_large_batches_only():
+    db = gaussian(8192, 128, 1)
+    s = DeviceStore(128, DistanceMetric.L2)
+    s.append(db)
+    s.search_flat(gaussian(4, 128, 2), 10)
+    assert s.last_counters()[0] == 0
+    s.search_flat(gaussian(64, 128, 2), 10)
+    assert s.last_counters()[0] == 64
+    s.close()
