@@ -105,48 +105,54 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   return d;
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct FilterArgs {
   const __nv_bfloat16* qb;  // [n_qblocks*128][kpad]
   const float* aux;         // [n_rows]
   uint32_t nq, n_rows, kpad;
   uint32_t n_qblocks, n_chunks, tiles_per_chunk, n_tiles;
-  uint32_t kprime;
   float coef;               // -2 (L2) or -1 (IP, cosine)
-  float* cand_score;        // [nq][n_chunks][kprime]
-  uint32_t* cand_row;       // [nq][n_chunks][kprime]
+  float* cand_score;        // [nq][n_chunks][KP]
+  uint32_t* cand_row;       // [nq][n_chunks][KP]
   float* chunk_tau;         // [nq][n_chunks]
   float* dbg_scores;        // optional [nq][n_rows]
 };
 
-template <int BN>
-struct FilterCfg {
-  static constexpr int STAGE_BYTES = BN * TF_BK * 2;
-  static constexpr int STAGES = (BN == 64) ? 16 : 8;
-  static constexpr int ACC_COLS = 2 * BN;  // two accumulator buffers
-};
+constexpr int TF_BN = 128;                        // database rows per tile (UMMA N)
+constexpr int TF_STAGE_BYTES = TF_BN * TF_BK * 2;  // 16 KB
+constexpr int TF_STAGES = 10;
 
-template <int BN>
+// KP   : candidates kept per (query, chunk); scores live in registers, rows in shared memory
+// NBUF : accumulator buffers in TMEM (2 when the A operand leaves room, else 1)
+template <int KP, int NBUF, bool DBG>
 __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
-  using Cfg = FilterCfg<BN>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve-up: [B stages][cand_score 128*kprime][cand_row 128*kprime][aux 2*BN][barriers][tmem ptr]
-  unsigned char* sb = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_cscore = reinterpret_cast<float*>(sb + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint32_t* s_crow = reinterpret_cast<uint32_t*>(s_cscore + 128 * a.kprime);
-  float* s_aux = reinterpret_cast<float*>(s_crow + 128 * a.kprime);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 2 * BN);
-  uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
-  uint64_t* empty = full + Cfg::STAGES;         // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = empty + Cfg::STAGES;     // [2]       MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;           // [2]       epilogue -> MMA
-  uint64_t* a_ready = acc_empty + 2;            // [1]       epilogue (A stored) -> MMA
+  // carve-up: [B stages][cand_row 128*KP][queue 2*16*128][aux 2*BN][barriers][tmem ptr]
+  // 1024-byte alignment for the 128B-swizzled tiles; plain pointer arithmetic on the __shared__
+  // array keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
+  unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t* s_crow = reinterpret_cast<uint32_t*>(sb + TF_STAGES * TF_STAGE_BYTES);
+  float* s_qs = reinterpret_cast<float*>(s_crow + 128 * KP);      // [16][128] queued scores
+  uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * 128);  // [16][128] queued columns
+  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 2 * TF_BN);
+  uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
+  uint64_t* empty = full + TF_STAGES;        // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = empty + TF_STAGES;    // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;        // [2]       epilogue -> MMA
+  uint64_t* a_ready = acc_empty + 2;         // [1]       epilogue (A stored) -> MMA
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t KB = a.kpad / TF_BK;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) {
+    for (int i = 0; i < TF_STAGES; ++i) {
       mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
@@ -165,66 +171,71 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_acc = tmem_base;                   // columns [0, 2*BN)
-  const uint32_t tmem_a = tmem_base + Cfg::ACC_COLS;     // columns [2*BN, 2*BN + kpad/2)
+  const uint32_t tmem_acc = tmem_base;                    // columns [0, NBUF*BN)
+  const uint32_t tmem_a = tmem_base + NBUF * TF_BN;       // columns [NBUF*BN, NBUF*BN + kpad/2)
 
   const uint32_t n_items = a.n_qblocks * a.n_chunks;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t chunk = item / a.n_qblocks;
-        const uint32_t t0 = chunk * a.tiles_per_chunk;
-        const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        for (uint32_t t = t0; t < t1; ++t) {
-          for (uint32_t kb = 0; kb < KB; ++kb) {
-            mbar_wait(empty + stage, phase ^ 1);
-            mbar_expect_tx(full + stage, Cfg::STAGE_BYTES);
-            tma_load_2d(sb + stage * Cfg::STAGE_BYTES, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * BN));
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+    // ===== TMA producer (warp-uniform control flow; one elected lane issues) =====
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint32_t chunk = item / a.n_qblocks;
+      const uint32_t t0 = chunk * a.tiles_per_chunk;
+      const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+      for (uint32_t t = t0; t < t1; ++t) {
+        for (uint32_t kb = 0; kb < KB; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full + stage, TF_STAGE_BYTES);
+            tma_load_2d(sb + stage * TF_STAGE_BYTES, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * TF_BN));
+          }
+          __syncwarp();
+          if (++stage == TF_STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
-      uint32_t stage = 0, phase = 0, acc_it = 0, a_phase = 0;
-      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const uint32_t chunk = item / a.n_qblocks;
-        const uint32_t t0 = chunk * a.tiles_per_chunk;
-        const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        mbar_wait(a_ready, a_phase);
-        a_phase ^= 1;
+    // ===== MMA issuer (warp-uniform control flow; one elected lane issues) =====
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TF_BN >> 3) << 17) | ((uint32_t)(TF_BM >> 4) << 24);
+    const uint64_t bdesc0 = make_b_desc(smem_u32(sb));
+    uint32_t stage = 0, phase = 0, acc_it = 0, a_phase = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const uint32_t chunk = item / a.n_qblocks;
+      const uint32_t t0 = chunk * a.tiles_per_chunk;
+      const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+      mbar_wait(a_ready, a_phase);
+      a_phase ^= 1;
+      tc_fence_after();
+      for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
+        const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
+        const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
+        mbar_wait(acc_empty + buf, (use & 1) ^ 1);
         tc_fence_after();
-        for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
-          const uint32_t buf = acc_it & 1;
-          mbar_wait(acc_empty + buf, ((acc_it >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem_acc + buf * TF_BN;
+        for (uint32_t kb = 0; kb < KB; ++kb) {
+          mbar_wait(full + stage, phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_acc + buf * BN;
-          for (uint32_t kb = 0; kb < KB; ++kb) {
-            mbar_wait(full + stage, phase);
-            tc_fence_after();
-            const uint64_t bdesc = make_b_desc(smem_u32(sb + stage * Cfg::STAGE_BYTES));
+          if (elect_one()) {
+            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
+            const uint32_t a_col = tmem_a + kb * (TF_BK / 2);
 #pragma unroll
             for (uint32_t k = 0; k < TF_BK / 16; ++k) {
               // A: 16 bf16 of K = 8 TMEM columns; B: 32 bytes further along the swizzled row
-              tc_mma_ts(d_tmem, tmem_a + kb * (TF_BK / 2) + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              tc_mma_ts(d_tmem, a_col + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
             }
-            tc_commit(empty + stage);  // smem slot free once these MMAs retire
-            if (++stage == Cfg::STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
+            tc_commit(empty + stage);                     // smem slot free once these MMAs retire
+            if (kb == KB - 1) tc_commit(acc_full + buf);  // accumulator ready for the epilogue
           }
-          tc_commit(acc_full + buf);  // accumulator ready for the epilogue
+          __syncwarp();
+          if (++stage == TF_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -234,9 +245,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
     const uint32_t qrow = quarter * 32 + lane;         // query row within the block == TMEM lane
     const uint32_t et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
     const uint32_t lane_addr = (quarter * 32) << 16;
-    const uint32_t kp = a.kprime;
-    float* my_score = s_cscore + qrow;                 // slot j at [j*128]
-    uint32_t* my_row = s_crow + qrow;
+    const float INF = __int_as_float(0x7f800000);
+    uint32_t* my_row = s_crow + qrow;                  // slot j at [j*128]
+    float* my_qs = s_qs + qrow;
+    uint32_t* my_qc = s_qc + qrow;
     uint32_t acc_it = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / a.n_qblocks;
@@ -257,74 +269,124 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
       }
-      for (uint32_t j = 0; j < kp; ++j) {
-        my_score[j * 128] = __int_as_float(0x7f800000);
+      // ---- per-query candidate set: KP scores in registers (unsorted), rows in smem ----
+      float sc[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        sc[j] = INF;
         my_row[j * 128] = ROW_NONE;
       }
-      float theta = __int_as_float(0x7f800000);  // current k'-th best score of this query in this chunk
+      float theta = INF;   // max of sc[] == the KP-th best score seen so far
+      int imax = 0;        // a slot holding theta
+      // additive per-column term for the first tile, fetched one tile ahead from here on
+      float aux_next = INF;
+      {
+        uint32_t c = t0 * TF_BN + et;
+        if (t0 < t1 && c < a.n_rows) aux_next = __ldg(a.aux + c);
+      }
       for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
-        const uint32_t buf = acc_it & 1;
-        const uint32_t col0 = t * BN;
-        // stage the per-column additive term (||x~||^2, 0, or +Inf for deleted / out-of-range rows)
-        if (et < BN) {
-          uint32_t c = col0 + et;
-          s_aux[buf * BN + et] = (c < a.n_rows) ? __ldg(a.aux + c) : __int_as_float(0x7f800000);
+        const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
+        const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
+        const uint32_t col0 = t * TF_BN;
+        float* aux_t = s_aux + (acc_it & 1) * TF_BN;
+        // per-column additive term (||x~||^2, 0, or +Inf for deleted / out-of-range rows)
+        aux_t[et] = aux_next;
+        {
+          uint32_t c = col0 + TF_BN + et;
+          aux_next = (t + 1 < t1 && c < a.n_rows) ? __ldg(a.aux + c) : INF;
         }
         epi_bar_sync();
-        mbar_wait(acc_full + buf, (acc_it >> 1) & 1);
+        mbar_wait(acc_full + buf, use & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int g = 0; g < BN / 32; ++g) {
-          float v[32];
-          tc_ld32(tmem_acc + lane_addr + buf * BN + g * 32, v);
-          tc_wait_ld();
-          const float4* ax = reinterpret_cast<const float4*>(s_aux + buf * BN + g * 32);
-          float best = __int_as_float(0x7f800000);
+        float v[TF_BN];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x = ax[j];
-            v[4 * j + 0] = fmaf(a.coef, v[4 * j + 0], x.x);
-            v[4 * j + 1] = fmaf(a.coef, v[4 * j + 1], x.y);
-            v[4 * j + 2] = fmaf(a.coef, v[4 * j + 2], x.z);
-            v[4 * j + 3] = fmaf(a.coef, v[4 * j + 3], x.w);
-            best = fminf(best, fminf(fminf(v[4 * j + 0], v[4 * j + 1]), fminf(v[4 * j + 2], v[4 * j + 3])));
-          }
-          if (a.dbg_scores && q_global < a.nq) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t c = col0 + g * 32 + j;
-              if (c < a.n_rows) a.dbg_scores[(size_t)q_global * a.n_rows + c] = v[j];
-            }
-          }
-          if (best < theta) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = v[j];
-              if (s < theta) {
-                // sorted insertion; equal scores keep the earlier (lower) row first
-                uint32_t p = kp - 1;
-                while (p > 0 && my_score[(p - 1) * 128] > s) {
-                  my_score[p * 128] = my_score[(p - 1) * 128];
-                  my_row[p * 128] = my_row[(p - 1) * 128];
-                  --p;
-                }
-                my_score[p * 128] = s;
-                my_row[p * 128] = col0 + g * 32 + j;
-                theta = my_score[(kp - 1) * 128];
-              }
-            }
-          }
-        }
-        // accumulator buffer drained
+        for (int g = 0; g < TF_BN / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF_BN + g * 32, v + g * 32);
+        tc_wait_ld();
+        // the accumulator now lives in registers: hand the TMEM buffer back before processing
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + buf);
+        // Gate four columns at a time (min of 4 against theta); survivors are queued in shared
+        // memory and inserted by one loop per 16-column segment, so the unrolled code stays small.
+        const float4* aux4 = reinterpret_cast<const float4*>(aux_t);
+        float4 ax[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ax[i] = aux4[i];
+#pragma unroll
+        for (int seg = 0; seg < TF_BN / 16; ++seg) {
+          float4 axn[4];
+          if (seg + 1 < TF_BN / 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) axn[i] = aux4[(seg + 1) * 4 + i];
+          }
+          uint32_t cnt = 0;
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int j = seg * 16 + g4 * 4;
+            const float s0 = fmaf(a.coef, v[j + 0], ax[g4].x);
+            const float s1 = fmaf(a.coef, v[j + 1], ax[g4].y);
+            const float s2 = fmaf(a.coef, v[j + 2], ax[g4].z);
+            const float s3 = fmaf(a.coef, v[j + 3], ax[g4].w);
+            if (DBG) {
+              v[j + 0] = s0;
+              v[j + 1] = s1;
+              v[j + 2] = s2;
+              v[j + 3] = s3;
+            }
+            if (fminf(fminf(s0, s1), fminf(s2, s3)) < theta) {
+              if (s0 < theta) { my_qs[cnt * 128] = s0; my_qc[cnt * 128] = col0 + j + 0; ++cnt; }
+              if (s1 < theta) { my_qs[cnt * 128] = s1; my_qc[cnt * 128] = col0 + j + 1; ++cnt; }
+              if (s2 < theta) { my_qs[cnt * 128] = s2; my_qc[cnt * 128] = col0 + j + 2; ++cnt; }
+              if (s3 < theta) { my_qs[cnt * 128] = s3; my_qc[cnt * 128] = col0 + j + 3; ++cnt; }
+            }
+          }
+#pragma unroll 1
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const float s = my_qs[i * 128];
+            if (s < theta) {
+              // replace the current worst, then find the new worst by a tree arg-max (no ordering
+              // is needed here: the merge kernel sorts; rows with s >= theta are exactly the rejected ones)
+              my_row[imax * 128] = my_qc[i * 128];
+              float mv[KP];
+              int mi[KP];
+#pragma unroll
+              for (int t2 = 0; t2 < KP; ++t2) {
+                sc[t2] = (t2 == imax) ? s : sc[t2];
+                mv[t2] = sc[t2];
+                mi[t2] = t2;
+              }
+#pragma unroll
+              for (int w = KP / 2; w >= 1; w >>= 1) {
+#pragma unroll
+                for (int t2 = 0; t2 < w; ++t2) {
+                  const bool gt = mv[t2 + w] > mv[t2];
+                  mv[t2] = gt ? mv[t2 + w] : mv[t2];
+                  mi[t2] = gt ? mi[t2 + w] : mi[t2];
+                }
+              }
+              theta = mv[0];
+              imax = mi[0];
+            }
+          }
+          if (seg + 1 < TF_BN / 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ax[i] = axn[i];
+          }
+        }
+        if (DBG && a.dbg_scores && q_global < a.nq) {
+#pragma unroll
+          for (int j = 0; j < TF_BN; ++j) {
+            uint32_t c = col0 + j;
+            if (c < a.n_rows) a.dbg_scores[(size_t)q_global * a.n_rows + c] = v[j];
+          }
+        }
       }
       // ---- chunk result ----
       if (q_global < a.nq) {
-        size_t base = ((size_t)q_global * a.n_chunks + chunk) * kp;
-        for (uint32_t j = 0; j < kp; ++j) {
-          a.cand_score[base + j] = my_score[j * 128];
+        size_t base = ((size_t)q_global * a.n_chunks + chunk) * KP;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          a.cand_score[base + j] = sc[j];
           a.cand_row[base + j] = my_row[j * 128];
         }
         a.chunk_tau[(size_t)q_global * a.n_chunks + chunk] = theta;
@@ -505,7 +567,7 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool tensor_path_supported(const scn_store* s, uint32_t k) { return s->kpad <= TF_MAX_KPAD && k <= 64 && s->rows >= 1; }
+bool tensor_path_supported(const scn_store* s, uint32_t k) { return s->kpad <= TF_MAX_KPAD && k <= 24 && s->rows >= 1; }
 
 static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   uint32_t cmax = std::max(1u, std::min(256u, n_tiles / 8));
@@ -523,13 +585,12 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   return 1;
 }
 
-template <int BN>
+template <int KP, int NBUF, bool DBG>
 static int32_t launch_filter(const CUtensorMap& tmap, const FilterArgs& fa, int grid, cudaStream_t stream) {
-  using Cfg = FilterCfg<BN>;
-  size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * fa.kprime * 8 + (size_t)2 * BN * 4 +
-                (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
-  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tensor_filter_kernel<BN><<<grid, TF_THREADS, smem, stream>>>(tmap, fa);
+  size_t smem = 1024 + (size_t)TF_STAGES * TF_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 + (size_t)2 * TF_BN * 4 +
+                (size_t)(2 * TF_STAGES + 5) * 8 + 16;
+  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tensor_filter_kernel<KP, NBUF, DBG><<<grid, TF_THREADS, smem, stream>>>(tmap, fa);
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -540,7 +601,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
-  const uint32_t BN = (s->kpad > 512) ? 64 : 128;
+  const uint32_t BN = TF_BN;
   const uint32_t n_rows = (uint32_t)s->rows;
   const uint32_t n_tiles = (n_rows + BN - 1) / BN;
   const uint32_t n_qb = (uint32_t)((nq + TF_BM - 1) / TF_BM);
@@ -548,9 +609,8 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   uint32_t n_chunks = pick_chunks(n_qb, n_tiles, (uint32_t)sms);
   uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-  uint32_t kprime = s->opt_overfetch > 0 ? (uint32_t)s->opt_overfetch : std::max(16u, round_up(k + k / 2 + 1, 8));
-  kprime = std::min(kprime, 96u);
-  if (kprime < k) return fail(SCN_ERR_INVALID_PARAMETERS, "overfetch %u is below k=%u", kprime, k);
+  // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
+  uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
   const uint32_t n_cand = n_chunks * kprime;
   const uint32_t n_pad = std::max(32u, next_pow2(n_cand));
   const uint32_t kpp = std::min(n_pad, std::max(32u, next_pow2(2 * k)));  // rows handed to the exact rerank
@@ -596,7 +656,6 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   fa.n_chunks = n_chunks;
   fa.tiles_per_chunk = tiles_per_chunk;
   fa.n_tiles = n_tiles;
-  fa.kprime = kprime;
   fa.coef = (s->metric == M_L2) ? -2.0f : -1.0f;
   fa.cand_score = d_cscore;
   fa.cand_row = d_crow;
@@ -604,7 +663,11 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   fa.dbg_scores = dbg_scores;
   int grid = (int)std::min<uint32_t>((uint32_t)sms, n_qb * n_chunks);
   if (prof) prof->begin("tensor_filter");
-  int32_t rc = (BN == 64) ? launch_filter<64>(tmap, fa, grid, stream) : launch_filter<128>(tmap, fa, grid, stream);
+  const bool two_buf = s->kpad <= 512;
+  int32_t rc;
+  if (dbg_scores) rc = two_buf ? launch_filter<16, 2, true>(tmap, fa, grid, stream) : launch_filter<16, 1, true>(tmap, fa, grid, stream);
+  else if (kprime == 16) rc = two_buf ? launch_filter<16, 2, false>(tmap, fa, grid, stream) : launch_filter<16, 1, false>(tmap, fa, grid, stream);
+  else rc = two_buf ? launch_filter<32, 2, false>(tmap, fa, grid, stream) : launch_filter<32, 1, false>(tmap, fa, grid, stream);
   if (prof) prof->end();
   SCN_TRY(rc);
 

@@ -193,6 +193,16 @@ int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store
   if (prop.major != 10)
     return fail(SCN_ERR_INTERNAL, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
                 prop.minor);
+  {
+    // Per-call scratch comes from the stream-ordered pool; keep freed blocks cached across the
+    // synchronisations of the blocking entry points instead of returning them to the driver.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   scn_store* s = new scn_store();
   s->device = device;
   s->dim = dim;

@@ -51,7 +51,7 @@ def test_filter_scores_match_bf16_emulation(metric, n, d, nq):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 300, 10), (6000, 128, 130, 10), (9999, 200, 77, 1), (5000, 64, 129, 32)])
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 300, 10), (6000, 128, 130, 10), (9999, 200, 77, 1), (5000, 64, 129, 24)])
 def test_tensor_path_bit_exact_vs_oracle(metric, n, d, nq, k):
     db, q = gaussian(n, d, 1234), gaussian(nq, d, 4321)
     s = DeviceStore(d, metric)
