@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.01)
         except Exception as e:  # NVML missing: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -331,8 +331,12 @@ def run_ours(args, wl):
             if name == "tensor_filter":
                 flops = 2.0 * nq * n_local * dim
                 ach = flops / (avg_ms * 1e-3) / 1e12
+                # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+                traffic = 10.39e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
                 roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                        "frac": ach / pk["bf16_sustained"], "traffic": traffic,
+                        "traffic_source": "profiles/r01_ncu_tensor_filter_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
+                        "algorithmic_flop": flops, "peak_source": pk["source"] + " (sustained bf16)",
                         "launch_ms": avg_ms, "share_of_step": share}
             elif name == "flat_exact_scan":
                 passes = (nq + 7) // 8
