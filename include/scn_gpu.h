@@ -175,8 +175,10 @@ SCN_API int32_t scn_last_timings(scn_store* s, const char** names, float* ms, ui
 /* Test hook: raw filter scores of the tensor-core path, out_scores[nq][rows] (host), where
  * score = aux[row] + c * (bf16(q) . mirror[row]) with c = -2 (L2) or -1 (inner product, cosine). */
 SCN_API int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t nq, float* out_scores);
-/* Counters of the last flat search: [0] queries served by the tensor path, [1] queries whose
- * certificate failed and were re-scanned exactly, [2] candidates reranked. */
+/* Counters of the last search. Flat: [0] queries served by the tensor path, [1] of those, queries
+ * whose first certificate failed (all their chunk candidates were then reranked), [2] queries that
+ * failed the second certificate too and were re-scanned exactly. HNSW (option "profile" = 1):
+ * [0] distance evaluations, [1] expansions. */
 SCN_API int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n);
 
 #ifdef __cplusplus

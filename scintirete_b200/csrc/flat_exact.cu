@@ -361,59 +361,67 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ v
                                                      const uint32_t* __restrict__ deleted, uint32_t pitch, uint32_t dim,
                                                      uint32_t n_rows, const float* __restrict__ q,
                                                      const uint32_t* __restrict__ cand, uint32_t ncand, uint32_t ncand_pad,
-                                                     uint32_t k, uint32_t row_base, uint64_t* __restrict__ out_keys) {
+                                                     uint32_t k, uint32_t row_base, const uint32_t* __restrict__ qlist,
+                                                     const uint32_t* __restrict__ nq_dev, uint32_t nq,
+                                                     uint64_t* __restrict__ out_keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);                    // [pitch]
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q + pitch);        // [ncand_pad]
   __shared__ float s_qnorm;
-  const uint32_t qi = blockIdx.x;
-  for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) s_q[i] = (i < dim) ? q[(size_t)qi * dim + i] : 0.0f;
-  __syncthreads();
-  if (METRIC == M_COS && threadIdx.x == 0) s_qnorm = exact_norm_thread(s_q, dim);
-  __syncthreads();
-  for (uint32_t c = threadIdx.x; c < ncand_pad; c += blockDim.x) {
-    uint64_t key = KEY_NONE;
-    if (c < ncand) {
-      uint32_t row = cand[(size_t)qi * ncand + c];
-      if (row < n_rows && !bit_test(deleted, row)) {
-        float acc = exact_acc_thread<METRIC>(s_q, vec + (size_t)row * pitch, pitch / 4);
-        float d = finish_distance<METRIC>(acc, METRIC == M_COS ? s_qnorm : 0.0f, METRIC == M_COS ? __ldg(norm + row) : 0.0f);
-        key = make_key(d, row + row_base);
+  const uint32_t n_slots = nq_dev ? min(*nq_dev, nq) : nq;
+  for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    const uint32_t qi = qlist ? qlist[slot] : slot;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) s_q[i] = (i < dim) ? q[(size_t)qi * dim + i] : 0.0f;
+    __syncthreads();
+    if (METRIC == M_COS && threadIdx.x == 0) s_qnorm = exact_norm_thread(s_q, dim);
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < ncand_pad; c += blockDim.x) {
+      uint64_t key = KEY_NONE;
+      if (c < ncand) {
+        uint32_t row = cand[(size_t)qi * ncand + c];
+        if (row < n_rows && !bit_test(deleted, row)) {
+          float acc = exact_acc_thread<METRIC>(s_q, vec + (size_t)row * pitch, pitch / 4);
+          float d = finish_distance<METRIC>(acc, METRIC == M_COS ? s_qnorm : 0.0f, METRIC == M_COS ? __ldg(norm + row) : 0.0f);
+          key = make_key(d, row + row_base);
+        }
       }
+      s_keys[c] = key;
     }
-    s_keys[c] = key;
-  }
-  block_bitonic_sort(s_keys, ncand_pad);
-  // drop duplicate rows (a candidate list may name a row twice): keys are identical -> adjacent
-  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) {
-    // position i of the de-duplicated sequence; lists are short, a serial prefix is fine
-    out_keys[(size_t)qi * k + i] = KEY_NONE;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t w = 0;
-    uint64_t prev = KEY_NONE;
-    for (uint32_t i = 0; i < ncand_pad && w < k; ++i) {
-      uint64_t v = s_keys[i];
-      if (v == KEY_NONE) break;
-      if (v != prev) out_keys[(size_t)qi * k + w++] = v;
-      prev = v;
+    block_bitonic_sort(s_keys, ncand_pad);
+    // emit the first k distinct keys (a candidate list may name a row twice: identical keys are adjacent)
+    for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out_keys[(size_t)qi * k + i] = KEY_NONE;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t w = 0;
+      uint64_t prev = KEY_NONE;
+      for (uint32_t i = 0; i < ncand_pad && w < k; ++i) {
+        uint64_t v = s_keys[i];
+        if (v == KEY_NONE) break;
+        if (v != prev) out_keys[(size_t)qi * k + w++] = v;
+        prev = v;
+      }
     }
   }
 }
 
+// Exact rerank of candidate rows cand[q][ncand] for all nq queries, or — with qlist / nq_dev — for
+// the listed queries only (device-resident count; the launch exits at once when it is zero).
 int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand, uint32_t k,
-                    uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream) {
+                    uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream, const uint32_t* d_qlist,
+                    const uint32_t* d_nq_dev) {
   if (nq == 0) return SCN_OK;
   uint32_t ncand_pad = std::max(32u, next_pow2(ncand));
   size_t smem = (size_t)s->pitch * 4 + (size_t)ncand_pad * 8;
   if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many rerank candidates (%u)", ncand);
+  const unsigned threads = std::min(128u, ncand_pad);
+  const unsigned grid = d_qlist ? (unsigned)std::min<uint64_t>(nq, 592) : (unsigned)nq;
 #define RR(MT)                                                                                                    \
   do {                                                                                                            \
     SCN_CUDA(cudaFuncSetAttribute(rerank_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    rerank_kernel<MT><<<(unsigned)nq, 128, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,   \
-                                                           (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k,      \
-                                                           (uint32_t)row_base, d_out_keys);                       \
+    rerank_kernel<MT><<<grid, threads, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,      \
+                                                       (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k,  \
+                                                       (uint32_t)row_base, d_qlist, d_nq_dev, (uint32_t)nq, d_out_keys); \
   } while (0)
   switch (s->metric) {
     case M_L2: RR(M_L2); break;

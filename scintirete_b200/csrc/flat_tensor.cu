@@ -435,7 +435,8 @@ __global__ void __launch_bounds__(128) merge_candidates_kernel(const float* __re
                                                                const uint32_t* __restrict__ cand_row,
                                                                const float* __restrict__ chunk_tau, uint32_t n_chunks,
                                                                uint32_t kprime, uint32_t n_pad, uint32_t kpp,
-                                                               uint32_t* __restrict__ out_rows, float* __restrict__ out_tau) {
+                                                               uint32_t* __restrict__ out_rows, float* __restrict__ out_tau,
+                                                               float* __restrict__ out_tau_chunks) {
   extern __shared__ __align__(16) unsigned char smem_merge[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_merge);  // [n_pad]
   const uint32_t q = blockIdx.x;
@@ -473,6 +474,7 @@ __global__ void __launch_bounds__(128) merge_candidates_kernel(const float* __re
     // rows never kept by a chunk (>= that chunk's tau) and rows dropped here (>= keys[kpp])
     float tau = __int_as_float(0x7f800000);
     for (uint32_t c = 0; c < n_chunks; ++c) tau = fminf(tau, chunk_tau[(size_t)q * n_chunks + c]);
+    out_tau_chunks[q] = tau;  // bound on rows no chunk kept: valid when ALL kept candidates are reranked
     if (kpp < n_pad && keys[kpp] != KEY_NONE) tau = fminf(tau, ord_f32((uint32_t)(keys[kpp] >> 32)));
     out_tau[q] = tau;
   }
@@ -490,10 +492,13 @@ __global__ void __launch_bounds__(128) merge_candidates_kernel(const float* __re
 // been missed. Anything else goes to the exact scan.
 __global__ void certify_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ tau, const float4* __restrict__ qstat,
                                const float* __restrict__ bounds, uint32_t nq, uint32_t k, uint32_t dim, uint32_t kpad,
-                               int metric, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count,
-                               unsigned long long* __restrict__ counters) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
+                               int metric, const uint32_t* __restrict__ qlist_in, const uint32_t* __restrict__ nq_in_dev,
+                               uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count,
+                               unsigned long long* __restrict__ counters, int counter_slot) {
+  const uint32_t n_slots = nq_in_dev ? min(*nq_in_dev, nq) : nq;
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const uint32_t q = qlist_in ? qlist_in[slot] : slot;
   const float INF = __int_as_float(0x7f800000);
   uint64_t kk = keys[(size_t)q * k + (k - 1)];
   float dk = (kk == KEY_NONE) ? INF : ord_f32((uint32_t)(kk >> 32));
@@ -540,8 +545,8 @@ __global__ void certify_kernel(const uint64_t* __restrict__ keys, const float* _
     fail_list[slot] = q;
   }
   if (counters) {
-    atomicAdd(counters + 0, 1ull);
-    if (!ok) atomicAdd(counters + 1, 1ull);
+    if (counter_slot == 1) atomicAdd(counters + 0, 1ull);
+    if (!ok) atomicAdd(counters + counter_slot, 1ull);
   }
 }
 
@@ -637,9 +642,13 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(scratch.alloc(&d_ctau, (size_t)nq * n_chunks));
   SCN_TRY(scratch.alloc(&d_tau, nq));
   SCN_TRY(scratch.alloc(&d_rows, (size_t)nq * kpp));
+  float* d_tau_chunks = nullptr;
+  uint32_t *d_fail2 = nullptr;
+  SCN_TRY(scratch.alloc(&d_tau_chunks, nq));
   SCN_TRY(scratch.alloc(&d_fail, nq));
-  SCN_TRY(scratch.alloc(&d_nfail, 1));
-  SCN_CUDA(cudaMemsetAsync(d_nfail, 0, sizeof(uint32_t), stream));
+  SCN_TRY(scratch.alloc(&d_fail2, nq));
+  SCN_TRY(scratch.alloc(&d_nfail, 2));
+  SCN_CUDA(cudaMemsetAsync(d_nfail, 0, 2 * sizeof(uint32_t), stream));
 
   if (prof) prof->begin("prep_queries");
   prep_queries_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(d_q, (uint32_t)nq, nq_pad, s->dim, s->kpad, d_qb, d_qstat);
@@ -673,7 +682,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
 
   if (prof) prof->begin("merge_candidates");
   merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_chunks, kprime, n_pad, kpp,
-                                                                            d_rows, d_tau);
+                                                                            d_rows, d_tau, d_tau_chunks);
   SCN_LAUNCHED();
   if (prof) prof->end();
 
@@ -683,12 +692,30 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
 
   if (prof) prof->begin("certify");
   certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau, d_qstat, s->d_bounds, (uint32_t)nq, k, s->dim,
-                                                                   s->kpad, s->metric, d_fail, d_nfail, s->d_counters);
+                                                                   s->kpad, s->metric, nullptr, nullptr, d_fail, d_nfail,
+                                                                   s->d_counters, 1);
   SCN_LAUNCHED();
   if (prof) prof->end();
 
-  // exact scan for whatever could not be certified (normally nothing: the kernel exits at once)
-  return flat_search_exact(s, d_q, d_fail, d_nfail, nq, k, row_base, d_out_keys, stream, prof);
+  // second chance for the few queries whose k'' rows were not enough: rerank every candidate the
+  // chunks kept (n_chunks * k') and certify against the chunk thresholds alone
+  if (n_cand > kpp) {
+    if (prof) prof->begin("rerank_exact_wide");
+    SCN_TRY(rerank_rows(s, d_q, nq, d_crow, n_cand, k, row_base, d_out_keys, stream, d_fail, d_nfail));
+    if (prof) prof->end();
+    if (prof) prof->begin("certify_wide");
+    certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau_chunks, d_qstat, s->d_bounds, (uint32_t)nq, k,
+                                                                     s->dim, s->kpad, s->metric, d_fail, d_nfail, d_fail2,
+                                                                     d_nfail + 1, s->d_counters, 2);
+    SCN_LAUNCHED();
+    if (prof) prof->end();
+  } else {
+    d_fail2 = d_fail;  // nothing wider to look at
+    SCN_CUDA(cudaMemcpyAsync(d_nfail + 1, d_nfail, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+  }
+
+  // exact scan for whatever could still not be certified (normally nothing: the kernel exits at once)
+  return flat_search_exact(s, d_q, d_fail2, d_nfail + 1, nq, k, row_base, d_out_keys, stream, prof);
 }
 
 int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys,

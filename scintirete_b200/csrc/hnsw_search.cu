@@ -1,9 +1,8 @@
 // hnsw_search.cu — K5: batched HNSW.Search (hnsw.go:292-350) — greedy descent through the upper
-// layers, layer-0 beam search (searchLayer, hnsw.go:487-557) and the top-k rerank, one warp per
-// query.
+// layers, layer-0 beam search (searchLayer, hnsw.go:487-557) and the top-k cut, one warp per query.
 //
 // Mapping of the reference's state onto the warp:
-//   candidates (W)  -> one sorted list of ef (key, row) pairs in shared memory;
+//   candidates (W)  -> one sorted list of ef (key, row) pairs in shared memory (double buffered);
 //                      key = ord(dist) << 32 | admission_seq << 1 | expanded  (stable: on equal
 //                      distance the earlier-admitted entry stays ahead, hnsw.go:675-686)
 //   dynamic (C)     -> the `expanded` bit: every live element of C is an un-expanded element of W
@@ -12,12 +11,22 @@
 //                      the first un-expanded entry of W" and the loop ends when there is none.
 //                      (Only exact float ties with W[ef-1] can make the two differ.)
 //   visited         -> open-addressing hash of row indices in shared memory (global-memory table
-//                      as the overflow path)
-//   Distance()      -> traversal: 128-bit coalesced row loads, FMA, warp-shuffle reduction
-//                      (ordering-only; L2 is compared squared); returned distances: recomputed in
-//                      the reference's exact sequential fp32 arithmetic (hnsw.go:330).
+//                      as the overflow pass)
+//   Distance()      -> one lane per neighbour: the lane walks its neighbour's row with 128-bit
+//                      loads and accumulates in the reference's exact sequential fp32 order, so all
+//                      (up to 32) neighbours of an expansion are evaluated concurrently, their loads
+//                      overlap, and every distance — hence the whole walk — is bit-identical to the
+//                      reference's. (The first version evaluated 4 rows at a time warp-cooperatively
+//                      with shuffle reductions and serialised ~6 memory latencies per expansion:
+//                      25 us per expansion at C1.)
+//   admission       -> the reference admits neighbours one by one against the current W[ef-1]
+//                      (strict <) and re-sorts; the result is the best ef of W u new under the
+//                      stable (dist, admission order) order, which is computed here in one step:
+//                      warp bitonic sort of the new keys + rank-based merge into the other buffer.
 // Per neighbour the reference's order of tests is kept: visited? -> deleted? (not marked visited,
 // not traversed) -> mark visited -> distance -> admit if |W| < ef or d < W[ef-1].d (strict).
+// The rerank of hnsw.go:317-347 recomputes the same distances and stably re-sorts an already
+// sorted list, so the first min(k, |W|) entries of W are the result.
 // Roofline: HBM random gather; algorithmic bytes per query = evals*dim*4 + hops*2M*4.
 #include "store.h"
 
@@ -53,86 +62,11 @@ struct HnswArgs {
   unsigned long long* stats;  // [0] distance evaluations, [1] expansions (optional)
 };
 
-template <int METRIC>
-__device__ __forceinline__ float traversal_finish(float acc, float qn, float xn) {
-  if (METRIC == M_L2) return acc;  // squared: same ordering as the reference's sqrt
-  if (METRIC == M_IP) return -acc;
-  if (qn == 0.0f || xn == 0.0f) return 1.0f;
-  float cs = acc / (qn * xn);
-  cs = fminf(1.0f, fmaxf(-1.0f, cs));
-  return 1.0f - cs;
+__host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t hash_size, bool global_hash) {
+  // wkey[2][ef_pad] u64 | snk[32] u64 | q[pitch] f32 | wrow[2][ef_pad] u32 | snr[32] u32 | hash
+  return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + (global_hash ? 0 : (size_t)hash_size * 4);
 }
 
-// Distances from the query (shared memory) to up to 4 rows at once; every lane returns all four
-// reduced sums. Rows equal to ROW_NONE are skipped (their result is unspecified).
-template <int METRIC>
-__device__ __forceinline__ void warp_dist4(const float* __restrict__ sq, const float* __restrict__ vec, uint32_t pitch,
-                                           const uint32_t r[4], int lane, float out[4]) {
-  const uint32_t p4 = pitch >> 2;
-  const float4* q4 = reinterpret_cast<const float4*>(sq);
-  const float4* x0 = reinterpret_cast<const float4*>(vec + (size_t)(r[0] == ROW_NONE ? 0 : r[0]) * pitch);
-  const float4* x1 = reinterpret_cast<const float4*>(vec + (size_t)(r[1] == ROW_NONE ? 0 : r[1]) * pitch);
-  const float4* x2 = reinterpret_cast<const float4*>(vec + (size_t)(r[2] == ROW_NONE ? 0 : r[2]) * pitch);
-  const float4* x3 = reinterpret_cast<const float4*>(vec + (size_t)(r[3] == ROW_NONE ? 0 : r[3]) * pitch);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-  for (uint32_t i = lane; i < p4; i += 32) {
-    float4 qv = q4[i];
-    float4 v0 = __ldg(x0 + i), v1 = __ldg(x1 + i), v2 = __ldg(x2 + i), v3 = __ldg(x3 + i);
-    if (METRIC == M_L2) {
-      float d;
-      d = qv.x - v0.x; a0 = fmaf(d, d, a0); d = qv.y - v0.y; a0 = fmaf(d, d, a0);
-      d = qv.z - v0.z; a0 = fmaf(d, d, a0); d = qv.w - v0.w; a0 = fmaf(d, d, a0);
-      d = qv.x - v1.x; a1 = fmaf(d, d, a1); d = qv.y - v1.y; a1 = fmaf(d, d, a1);
-      d = qv.z - v1.z; a1 = fmaf(d, d, a1); d = qv.w - v1.w; a1 = fmaf(d, d, a1);
-      d = qv.x - v2.x; a2 = fmaf(d, d, a2); d = qv.y - v2.y; a2 = fmaf(d, d, a2);
-      d = qv.z - v2.z; a2 = fmaf(d, d, a2); d = qv.w - v2.w; a2 = fmaf(d, d, a2);
-      d = qv.x - v3.x; a3 = fmaf(d, d, a3); d = qv.y - v3.y; a3 = fmaf(d, d, a3);
-      d = qv.z - v3.z; a3 = fmaf(d, d, a3); d = qv.w - v3.w; a3 = fmaf(d, d, a3);
-    } else {
-      a0 = fmaf(qv.x, v0.x, a0); a0 = fmaf(qv.y, v0.y, a0); a0 = fmaf(qv.z, v0.z, a0); a0 = fmaf(qv.w, v0.w, a0);
-      a1 = fmaf(qv.x, v1.x, a1); a1 = fmaf(qv.y, v1.y, a1); a1 = fmaf(qv.z, v1.z, a1); a1 = fmaf(qv.w, v1.w, a1);
-      a2 = fmaf(qv.x, v2.x, a2); a2 = fmaf(qv.y, v2.y, a2); a2 = fmaf(qv.z, v2.z, a2); a2 = fmaf(qv.w, v2.w, a2);
-      a3 = fmaf(qv.x, v3.x, a3); a3 = fmaf(qv.y, v3.y, a3); a3 = fmaf(qv.z, v3.z, a3); a3 = fmaf(qv.w, v3.w, a3);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-  }
-  out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
-}
-
-// Evaluates the traversal distance of the `ns` rows held by lanes [0, ns) (value `nb`); lane j
-// receives the distance of its own row.
-template <int METRIC>
-__device__ __forceinline__ float eval_rows(const HnswArgs& a, const float* sq, float qn, uint32_t nb, uint32_t ns,
-                                           int lane) {
-  float mine = 0.0f;
-  for (uint32_t t = 0; t < ns; t += 4) {
-    uint32_t r[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      uint32_t v = __shfl_sync(0xffffffffu, nb, (t + u) & 31);
-      r[u] = (t + u < ns) ? v : ROW_NONE;
-    }
-    float d[4];
-    warp_dist4<METRIC>(sq, a.vec, a.pitch, r, lane, d);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if ((uint32_t)lane == t + u && t + u < ns) {
-        float xn = (METRIC == M_COS) ? __ldg(a.norm + r[u]) : 0.0f;
-        mine = traversal_finish<METRIC>(d[u], qn, xn);
-      }
-    }
-  }
-  return mine;
-}
-
-template <bool USE_GLOBAL>
 __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t hash_size, uint32_t row) {
   uint32_t h = __umulhi(row * 2654435761u, hash_size);
   const uint32_t key = row + 1;
@@ -145,32 +79,38 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t hash_size
   return false;  // table full (guarded against by the overflow check)
 }
 
+// The reference's Distance(query, row) for this lane's row, bit for bit.
+template <int METRIC>
+__device__ __forceinline__ float lane_distance(const HnswArgs& a, const float* sq, float qn, uint32_t row) {
+  float acc = exact_acc_thread<METRIC>(sq, a.vec + (size_t)row * a.pitch, a.pitch >> 2);
+  return finish_distance<METRIC>(acc, qn, METRIC == M_COS ? __ldg(a.norm + row) : 0.0f);
+}
+
 template <int METRIC, bool USE_GLOBAL>
 __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_hnsw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t warp_global = blockIdx.x * HNSW_WARPS + warp;
   const uint32_t warps_total = gridDim.x * HNSW_WARPS;
-  // per-warp carve-up: q[pitch] | wkey[ef_pad] | wrow[ef_pad] | hash[hash_size] (smem mode)
-  const size_t per_warp = (size_t)a.pitch * 4 + (size_t)a.ef_pad * 12 + (USE_GLOBAL ? 0 : (size_t)a.hash_size * 4);
-  unsigned char* base = smem_raw + per_warp * warp;
-  uint64_t* wkey = reinterpret_cast<uint64_t*>(base);
-  float* sq = reinterpret_cast<float*>(wkey + a.ef_pad);
-  uint32_t* wrow = reinterpret_cast<uint32_t*>(sq + a.pitch);
-  uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : (wrow + a.ef_pad);
+  unsigned char* base = smem_hnsw + hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, USE_GLOBAL) * warp;
+  uint64_t* wkey0 = reinterpret_cast<uint64_t*>(base);
+  uint64_t* wkey1 = wkey0 + a.ef_pad;
+  uint64_t* snk = wkey1 + a.ef_pad;                              // sorted new keys
+  float* sq = reinterpret_cast<float*>(snk + 32);
+  uint32_t* wrow0 = reinterpret_cast<uint32_t*>(sq + a.pitch);
+  uint32_t* wrow1 = wrow0 + a.ef_pad;
+  uint32_t* snr = wrow1 + a.ef_pad;                              // rows of the sorted new keys
+  uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : (snr + 32);
   const uint32_t ef = a.ef;
   const uint32_t nq = a.qlist ? min(*a.nq_dev, a.nq) : a.nq;
+  const float INF = __int_as_float(0x7f800000);
   unsigned long long evals = 0, hops = 0;
 
   for (uint32_t qslot = warp_global; qslot < nq; qslot += warps_total) {
     const uint32_t qi = a.qlist ? a.qlist[qslot] : qslot;
     __syncwarp();
     for (uint32_t i = lane; i < a.pitch; i += 32) sq[i] = (i < a.dim) ? a.q[(size_t)qi * a.dim + i] : 0.0f;
-    if (USE_GLOBAL) {
-      for (uint32_t i = lane; i < a.hash_size; i += 32) hash[i] = HASH_EMPTY;
-    } else {
-      for (uint32_t i = lane; i < a.hash_size; i += 32) hash[i] = HASH_EMPTY;
-    }
+    for (uint32_t i = lane; i < a.hash_size; i += 32) hash[i] = HASH_EMPTY;
     __syncwarp();
     float qn = 0.0f;
     if (METRIC == M_COS) {
@@ -178,21 +118,20 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
       qn = __shfl_sync(0xffffffffu, qn, 0);
     }
 
-    uint32_t n_out = 0;
+    uint64_t* wkey = wkey0;   // current list
+    uint32_t* wrow = wrow0;
+    uint64_t* okey = wkey1;   // merge target
+    uint32_t* orow = wrow1;
     uint32_t cnt = 0;
     bool overflow = false;
     uint32_t cur = a.entry_row;
     const bool have_entry = (cur != ROW_NONE) && (cur < a.n_rows) && !bit_test(a.deleted, cur) && a.max_layer >= 0;
     if (have_entry) {
       // ---- entry distance -------------------------------------------------------------------
-      float dcur;
-      {
-        uint32_t r[4] = {cur, ROW_NONE, ROW_NONE, ROW_NONE};
-        float d[4];
-        warp_dist4<METRIC>(sq, a.vec, a.pitch, r, lane, d);
-        dcur = traversal_finish<METRIC>(d[0], qn, METRIC == M_COS ? __ldg(a.norm + cur) : 0.0f);
-        ++evals;
-      }
+      float dcur = 0.0f;
+      if (lane == 0) dcur = lane_distance<METRIC>(a, sq, qn, cur);
+      dcur = __shfl_sync(0xffffffffu, dcur, 0);
+      ++evals;
       // ---- greedy descent, layers maxLayer..1 with numClosest = 1 (hnsw.go:309-311) -----------
       for (int layer = a.max_layer; layer >= 1; --layer) {
         for (;;) {
@@ -204,15 +143,11 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
           for (uint32_t c0 = 0; c0 < a.su; c0 += 32) {
             uint32_t nb = (c0 + lane < a.su) ? __ldg(list + c0 + lane) : ROW_NONE;
             bool ok = (nb != ROW_NONE) && !bit_test(a.deleted, nb);
-            uint32_t mask = __ballot_sync(0xffffffffu, ok);
-            uint32_t ns = __popc(mask);
-            if (!ns) continue;
-            uint32_t src = __fns(mask, 0, lane + 1);
-            uint32_t nbj = __shfl_sync(0xffffffffu, nb, src & 31);
-            float dj = eval_rows<METRIC>(a, sq, qn, nbj, ns, lane);
-            evals += ns;
-            // first strict minimum in list order (sequential `d < W[0].d` updates)
-            float dm = ((uint32_t)lane < ns) ? dj : __int_as_float(0x7f800000);
+            float d = INF;
+            if (ok) d = lane_distance<METRIC>(a, sq, qn, nb);
+            evals += __popc(__ballot_sync(0xffffffffu, ok));
+            // first strict minimum in list order (the reference's sequential `d < W[0].d` updates)
+            float dm = (ok && d == d) ? d : INF;
             uint32_t im = lane;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -225,7 +160,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
             }
             if (dm < best) {
               best = dm;
-              best_row = __shfl_sync(0xffffffffu, nbj, im);
+              best_row = __shfl_sync(0xffffffffu, nb, im);
             }
           }
           if (best_row == cur) break;
@@ -234,14 +169,13 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
         }
       }
       // ---- layer 0 beam (hnsw.go:314, 487-557) ---------------------------------------------
-      uint32_t seq = 0, visited = 1;
+      uint32_t seq = 1, visited = 1;
       if (lane == 0) {
-        wkey[0] = ((uint64_t)f32_ord(dcur) << 32) | ((uint64_t)(seq) << 1);
+        wkey[0] = ((uint64_t)f32_ord(dcur) << 32);
         wrow[0] = cur;
       }
-      seq = 1;
       cnt = 1;
-      visited_insert<USE_GLOBAL>(hash, a.hash_size, cur);
+      visited_insert(hash, a.hash_size, cur);
       __syncwarp();
       for (;;) {
         // closest un-expanded entry of W
@@ -272,57 +206,85 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
           // reference order: visited? -> deleted? -> mark visited. A deleted row is never
           // inserted, so testing `deleted` first and inserting only live rows is equivalent.
           if (ok) ok = !bit_test(a.deleted, nb);
-          if (ok) ok = visited_insert<USE_GLOBAL>(hash, a.hash_size, nb);
-          uint32_t mask = __ballot_sync(0xffffffffu, ok);
-          uint32_t ns = __popc(mask);
+          if (ok) ok = visited_insert(hash, a.hash_size, nb);
+          const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+          const uint32_t ns = __popc(mask);
           if (!ns) continue;
           visited += ns;
-          uint32_t src = __fns(mask, 0, lane + 1);
-          uint32_t nbj = __shfl_sync(0xffffffffu, nb, src & 31);
-          float dj = eval_rows<METRIC>(a, sq, qn, nbj, ns, lane);
           evals += ns;
-          // sequential admission in adjacency order (hnsw.go:536-546)
-          for (uint32_t j = 0; j < ns; ++j) {
-            float d = __shfl_sync(0xffffffffu, dj, j);
-            uint32_t row = __shfl_sync(0xffffffffu, nbj, j);
-            uint32_t od = f32_ord(d);
-            if (cnt >= ef && !(od < (uint32_t)(wkey[ef - 1] >> 32))) continue;  // strict <, NaN never admitted
-            uint64_t key = ((uint64_t)od << 32) | ((uint64_t)seq << 1);
-            ++seq;
-            // position: after every entry with distance <= d (stable tail insertion)
-            uint32_t pos = 0;
-            for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
-              uint32_t i = b0 + lane;
-              bool lt = (i < cnt) && ((wkey[i] >> 32) <= od);
-              pos += __popc(__ballot_sync(0xffffffffu, lt));
-            }
-            const uint32_t last = (cnt < ef) ? cnt : ef - 1;  // destination of the last shifted entry
-            for (int b0 = (int)(last / 32) * 32; b0 >= 0; b0 -= 32) {
-              uint32_t i = b0 + lane;
-              bool mv = (i <= last) && (i > pos);
-              uint64_t kv = 0;
-              uint32_t rv = 0;
-              if (mv) {
-                kv = wkey[i - 1];
-                rv = wrow[i - 1];
+          float d = INF;
+          if (ok) d = lane_distance<METRIC>(a, sq, qn, nb);
+          // admission (hnsw.go:536-542): while |W| < ef everything enters; once full only
+          // d < W[ef-1].d (strict; a NaN never passes). Entering while the list is not full and
+          // being pushed out later is the same as losing the final cut of the merge below.
+          const uint32_t od = f32_ord(d);
+          bool in = ok;
+          if (in && cnt >= ef) in = od < (uint32_t)(wkey[ef - 1] >> 32);
+          // stable admission order = adjacency order
+          const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+          uint64_t key = in ? (((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1)) : KEY_NONE;
+          uint32_t row = nb;
+          seq += ns;
+          const uint32_t nn = __popc(__ballot_sync(0xffffffffu, in));
+          if (!nn) continue;
+          // ---- warp bitonic sort of the new keys (ascending; KEY_NONE sinks to the end) ----
+#pragma unroll
+          for (int ks = 2; ks <= 32; ks <<= 1) {
+#pragma unroll
+            for (int j = ks >> 1; j > 0; j >>= 1) {
+              const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+              const uint32_t orw = __shfl_xor_sync(0xffffffffu, row, j);
+              const bool up = ((lane & ks) == 0);
+              const bool lower = ((lane & j) == 0);
+              const bool take = (lower == up) ? (other < key) : (other > key);
+              if (take) {
+                key = other;
+                row = orw;
               }
-              __syncwarp();
-              if (mv) {
-                wkey[i] = kv;
-                wrow[i] = rv;
-              }
-              __syncwarp();
             }
-            if (lane == 0) {
-              wkey[pos] = key;
-              wrow[pos] = row;
-            }
-            if (cnt < ef) ++cnt;
-            __syncwarp();
           }
+          snk[lane] = key;
+          snr[lane] = row;
+          __syncwarp();
+          // ---- rank-based merge of W[0..cnt) and snk[0..nn) into the other buffer ----------
+          // old entry i moves to i + #{new < it}; new entry j moves to j + #{old < it}
+          for (uint32_t i = lane; i < cnt; i += 32) {
+            const uint64_t kv = wkey[i];
+            uint32_t lo = 0, hi = nn;
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (snk[mid] < kv) lo = mid + 1;
+              else hi = mid;
+            }
+            const uint32_t pos = i + lo;
+            if (pos < ef) {
+              okey[pos] = kv;
+              orow[pos] = wrow[i];
+            }
+          }
+          if ((uint32_t)lane < nn) {
+            uint32_t lo = 0, hi = cnt;
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (wkey[mid] < key) lo = mid + 1;
+              else hi = mid;
+            }
+            const uint32_t pos = lane + lo;
+            if (pos < ef) {
+              okey[pos] = key;
+              orow[pos] = row;
+            }
+          }
+          cnt = min(ef, cnt + nn);
+          __syncwarp();
+          uint64_t* tk = wkey;
+          wkey = okey;
+          okey = tk;
+          uint32_t* tr = wrow;
+          wrow = orow;
+          orow = tr;
         }
       }
-      n_out = min(a.k, cnt);
     }
 
     if (overflow && !USE_GLOBAL) {
@@ -333,43 +295,15 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
       continue;  // the overflow pass will produce this query's results
     }
 
-    // ---- rerank (hnsw.go:317-347): exact distances of the first n_out candidates, stable sort ----
-    const uint32_t np = max(32u, 1u << (32 - __clz(max(n_out, 1u) - 1)));
+    // ---- result: the first min(k, |W|) entries, already in (distance, admission) order --------
+    const uint32_t n_out = min(a.k, cnt);
     __syncwarp();
-    for (uint32_t i0 = 0; i0 < np; i0 += 32) {
-      uint32_t i = i0 + lane;
-      uint64_t key = KEY_NONE;
-      if (i < n_out) {
-        uint32_t row = wrow[i];
-        float acc = exact_acc_thread<METRIC>(sq, a.vec + (size_t)row * a.pitch, a.pitch >> 2);
-        float d = finish_distance<METRIC>(acc, qn, METRIC == M_COS ? __ldg(a.norm + row) : 0.0f);
-        key = ((uint64_t)f32_ord(d) << 32) | i;
-      }
-      __syncwarp();
-      if (i < a.ef_pad) wkey[i] = key;
-    }
-    __syncwarp();
-    for (uint32_t size = 2; size <= np; size <<= 1) {
-      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-        for (uint32_t t = lane; t < np / 2; t += 32) {
-          uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-          bool up = ((lo & size) == 0);
-          uint64_t x = wkey[lo], y = wkey[hi];
-          if ((x > y) == up) {
-            wkey[lo] = y;
-            wkey[hi] = x;
-          }
-        }
-        __syncwarp();
-      }
-    }
     for (uint32_t i = lane; i < a.k; i += 32) {
       uint64_t id = 0;
-      float d = __int_as_float(0x7f800000);
+      float d = INF;
       if (i < n_out) {
-        uint64_t key = wkey[i];
-        id = a.ids[wrow[(uint32_t)key]];
-        d = ord_f32((uint32_t)(key >> 32));
+        id = a.ids[wrow[i]];
+        d = ord_f32((uint32_t)(wkey[i] >> 32));
       }
       a.out_ids[(size_t)qi * a.k + i] = id;
       a.out_dist[(size_t)qi * a.k + i] = d;
@@ -385,8 +319,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
 template <int METRIC>
 static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
   // pass 1: shared-memory visited table
-  const size_t per_warp = (size_t)a.pitch * 4 + (size_t)a.ef_pad * 12 + (size_t)a.hash_size * 4;
-  const size_t smem = per_warp * HNSW_WARPS;
+  const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false) * HNSW_WARPS;
   SCN_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false>, HNSW_WARPS * 32, smem));
@@ -410,7 +343,7 @@ static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& s
   b.hash_size = std::max<uint32_t>(b.hash_size, 1024u);
   const int grid2 = std::min<int>(sms, (int)blocks_needed);
   SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * HNSW_WARPS * b.hash_size));
-  const size_t smem2 = ((size_t)a.pitch * 4 + (size_t)a.ef_pad * 12) * HNSW_WARPS;
+  const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true) * HNSW_WARPS;
   SCN_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   if (prof) prof->begin("hnsw_search_overflow");
   hnsw_search_kernel<METRIC, true><<<grid2, HNSW_WARPS * 32, smem2, stream>>>(b);
@@ -456,8 +389,7 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
   a.stats = s->opt_profile ? s->d_counters : nullptr;
   // shrink the table until at least one block fits
-  while ((((size_t)a.pitch * 4 + (size_t)a.ef_pad * 12 + (size_t)a.hash_size * 4) * HNSW_WARPS) > 200 * 1024 &&
-         a.hash_size > 1024)
+  while (hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false) * HNSW_WARPS > 200 * 1024 && a.hash_size > 1024)
     a.hash_size = round_up(a.hash_size / 2, 512);
   int32_t rc;
   switch (s->metric) {

@@ -163,7 +163,8 @@ int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t
                            uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof);
 bool tensor_path_supported(const scn_store* s, uint32_t k);
 int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t* d_cand_rows, uint32_t ncand,
-                    uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream);
+                    uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream,
+                    const uint32_t* d_qlist = nullptr, const uint32_t* d_nq_dev = nullptr);
 int32_t tensor_debug_scores(scn_store* s, const float* d_q, uint64_t nq, float* d_scores, cudaStream_t stream);
 int32_t mark_aux_deleted(scn_store* s, const uint32_t* h_rows, uint32_t n, cudaStream_t stream);
 int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
