@@ -26,7 +26,7 @@ namespace scn {
 
 constexpr int TF_BM = 128;        // queries per CTA (UMMA M)
 constexpr int TF_BK = 64;         // bf16 per smem K block = one 128-byte swizzle row
-constexpr int TF_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (TMEM lane quarters 2,3,0,1)
+constexpr int TF_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2..: epilogue, 4*EW warps (TMEM lane quarters 2,3,0,1,...)
 constexpr int TF_MAX_KPAD = 768;  // A operand must fit TMEM next to the accumulators
 
 // ---- PTX helpers --------------------------------------------------------------------------------
@@ -127,19 +127,22 @@ constexpr int TF_BN = 128;                        // database rows per tile (UMM
 constexpr int TF_STAGE_BYTES = TF_BN * TF_BK * 2;  // 16 KB
 constexpr int TF_STAGES = 10;
 
-// KP   : candidates kept per (query, chunk); scores live in registers, rows in shared memory
+// KP   : candidates kept per (query, chunk, column slice); scores live in registers, rows in smem
 // NBUF : accumulator buffers in TMEM (2 when the A operand leaves room, else 1)
-template <int KP, int NBUF, bool DBG>
-__global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
+// EW   : epilogue warps per TMEM lane quarter; each owns a slice of 128/EW columns of every tile.
+//        Short K (small dim) makes the MMA of a tile cheaper than its gate, so more warps gate.
+template <int KP, int NBUF, int EW, bool DBG>
+__global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve-up: [B stages][cand_row 128*KP][queue 2*16*128][aux 2*BN][barriers][tmem ptr]
+  // carve-up: [B stages][cand_row 128*EW*KP][queue 2*16*128*EW][aux 2*BN][barriers][tmem ptr]
   // 1024-byte alignment for the 128B-swizzled tiles; plain pointer arithmetic on the __shared__
   // array keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
   unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint32_t* s_crow = reinterpret_cast<uint32_t*>(sb + TF_STAGES * TF_STAGE_BYTES);
-  float* s_qs = reinterpret_cast<float*>(s_crow + 128 * KP);      // [16][128] queued scores
-  uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * 128);  // [16][128] queued columns
-  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * 128);
+  constexpr int ET = 128 * EW;                                     // epilogue threads
+  float* s_qs = reinterpret_cast<float*>(s_crow + ET * KP);        // [16][ET] queued scores
+  uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * ET);    // [16][ET] queued columns
+  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 2 * TF_BN);
   uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
   uint64_t* empty = full + TF_STAGES;        // [STAGES]  MMA -> TMA
@@ -158,9 +161,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, 4);  // one arrive per epilogue warp
+      mbar_init(acc_empty + i, 4 * EW);  // one arrive per epilogue warp
     }
-    mbar_init(a_ready, 4);
+    mbar_init(a_ready, 4 * EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns (one CTA per SM)
@@ -243,12 +246,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
     // ===== epilogue warps: thread <-> query (TMEM lane) =====
     const uint32_t quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const uint32_t qrow = quarter * 32 + lane;         // query row within the block == TMEM lane
-    const uint32_t et = (warp - 2) * 32 + lane;        // 0..127 among epilogue threads
+    const uint32_t et = (warp - 2) * 32 + lane;        // 0..ET-1 among epilogue threads
+    const uint32_t slice = (warp - 2) >> 2;            // which 128/EW columns of a tile this warp gates
+    constexpr int CW = TF_BN / EW;                     // columns per warp
     const uint32_t lane_addr = (quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
-    uint32_t* my_row = s_crow + qrow;                  // slot j at [j*128]
-    float* my_qs = s_qs + qrow;
-    uint32_t* my_qc = s_qc + qrow;
+    uint32_t* my_row = s_crow + slice * 128 + qrow;    // slot j at [j*ET]
+    float* my_qs = s_qs + slice * 128 + qrow;
+    uint32_t* my_qc = s_qc + slice * 128 + qrow;
     uint32_t acc_it = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / a.n_qblocks;
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
       {
         const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)q_global * a.kpad);
         const uint32_t n16 = a.kpad / 8;  // 16-byte groups = 4 TMEM columns each
-        for (uint32_t i = 0; i < n16; ++i) {
+        for (uint32_t i = slice; i < n16; i += EW) {  // the EW warps of a quarter share the copy
           uint4 v = __ldg(src + i);
           tc_st4(tmem_a + lane_addr + i * 4, v.x, v.y, v.z, v.w);
         }
@@ -274,13 +279,13 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
         sc[j] = INF;
-        my_row[j * 128] = ROW_NONE;
+        my_row[j * ET] = ROW_NONE;
       }
       float theta = INF;   // max of sc[] == the KP-th best score seen so far
       int imax = 0;        // a slot holding theta
       // additive per-column term for the first tile, fetched one tile ahead from here on
       float aux_next = INF;
-      {
+      if (et < TF_BN) {
         uint32_t c = t0 * TF_BN + et;
         if (t0 < t1 && c < a.n_rows) aux_next = __ldg(a.aux + c);
       }
@@ -290,17 +295,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
         const uint32_t col0 = t * TF_BN;
         float* aux_t = s_aux + (acc_it & 1) * TF_BN;
         // per-column additive term (||x~||^2, 0, or +Inf for deleted / out-of-range rows)
-        aux_t[et] = aux_next;
-        {
+        if (et < TF_BN) {
+          aux_t[et] = aux_next;
           uint32_t c = col0 + TF_BN + et;
           aux_next = (t + 1 < t1 && c < a.n_rows) ? __ldg(a.aux + c) : INF;
         }
-        epi_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
         mbar_wait(acc_full + buf, use & 1);
         tc_fence_after();
-        float v[TF_BN];
+        float v[CW];
 #pragma unroll
-        for (int g = 0; g < TF_BN / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF_BN + g * 32, v + g * 32);
+        for (int g = 0; g < CW / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF_BN + slice * CW + g * 32, v + g * 32);
         tc_wait_ld();
         // the accumulator now lives in registers: hand the TMEM buffer back before processing
         tc_fence_before();
@@ -308,14 +313,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
         if (lane == 0) mbar_arrive(acc_empty + buf);
         // Gate four columns at a time (min of 4 against theta); survivors are queued in shared
         // memory and inserted by one loop per 16-column segment, so the unrolled code stays small.
-        const float4* aux4 = reinterpret_cast<const float4*>(aux_t);
+        const float4* aux4 = reinterpret_cast<const float4*>(aux_t + slice * CW);
+        const uint32_t colw = col0 + slice * CW;  // first column of this warp's slice
         float4 ax[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) ax[i] = aux4[i];
 #pragma unroll
-        for (int seg = 0; seg < TF_BN / 16; ++seg) {
+        for (int seg = 0; seg < CW / 16; ++seg) {
           float4 axn[4];
-          if (seg + 1 < TF_BN / 16) {
+          if (seg + 1 < CW / 16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) axn[i] = aux4[(seg + 1) * 4 + i];
           }
@@ -334,19 +340,19 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
               v[j + 3] = s3;
             }
             if (fminf(fminf(s0, s1), fminf(s2, s3)) < theta) {
-              if (s0 < theta) { my_qs[cnt * 128] = s0; my_qc[cnt * 128] = col0 + j + 0; ++cnt; }
-              if (s1 < theta) { my_qs[cnt * 128] = s1; my_qc[cnt * 128] = col0 + j + 1; ++cnt; }
-              if (s2 < theta) { my_qs[cnt * 128] = s2; my_qc[cnt * 128] = col0 + j + 2; ++cnt; }
-              if (s3 < theta) { my_qs[cnt * 128] = s3; my_qc[cnt * 128] = col0 + j + 3; ++cnt; }
+              if (s0 < theta) { my_qs[cnt * ET] = s0; my_qc[cnt * ET] = colw + j + 0; ++cnt; }
+              if (s1 < theta) { my_qs[cnt * ET] = s1; my_qc[cnt * ET] = colw + j + 1; ++cnt; }
+              if (s2 < theta) { my_qs[cnt * ET] = s2; my_qc[cnt * ET] = colw + j + 2; ++cnt; }
+              if (s3 < theta) { my_qs[cnt * ET] = s3; my_qc[cnt * ET] = colw + j + 3; ++cnt; }
             }
           }
 #pragma unroll 1
           for (uint32_t i = 0; i < cnt; ++i) {
-            const float s = my_qs[i * 128];
+            const float s = my_qs[i * ET];
             if (s < theta) {
               // replace the current worst, then find the new worst by a tree arg-max (no ordering
               // is needed here: the merge kernel sorts; rows with s >= theta are exactly the rejected ones)
-              my_row[imax * 128] = my_qc[i * 128];
+              my_row[imax * ET] = my_qc[i * ET];
               float mv[KP];
               int mi[KP];
 #pragma unroll
@@ -368,28 +374,30 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tensor_filter_kernel(const __gr
               imax = mi[0];
             }
           }
-          if (seg + 1 < TF_BN / 16) {
+          if (seg + 1 < CW / 16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) ax[i] = axn[i];
           }
         }
         if (DBG && a.dbg_scores && q_global < a.nq) {
 #pragma unroll
-          for (int j = 0; j < TF_BN; ++j) {
-            uint32_t c = col0 + j;
+          for (int j = 0; j < CW; ++j) {
+            uint32_t c = colw + j;
             if (c < a.n_rows) a.dbg_scores[(size_t)q_global * a.n_rows + c] = v[j];
           }
         }
       }
       // ---- chunk result ----
       if (q_global < a.nq) {
-        size_t base = ((size_t)q_global * a.n_chunks + chunk) * KP;
+        // every (chunk, column slice) pair is its own candidate list: n_chunks*EW lists per query
+        const size_t vchunk = (size_t)chunk * EW + slice;
+        size_t base = ((size_t)q_global * a.n_chunks * EW + vchunk) * KP;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           a.cand_score[base + j] = sc[j];
-          a.cand_row[base + j] = my_row[j * 128];
+          a.cand_row[base + j] = my_row[j * ET];
         }
-        a.chunk_tau[(size_t)q_global * a.n_chunks + chunk] = theta;
+        a.chunk_tau[(size_t)q_global * a.n_chunks * EW + vchunk] = theta;
       }
       // all MMAs of this item have retired (the last acc_full was waited on), so A may be rewritten
     }
@@ -590,12 +598,12 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   return 1;
 }
 
-template <int KP, int NBUF, bool DBG>
+template <int KP, int NBUF, int EW, bool DBG>
 static int32_t launch_filter(const CUtensorMap& tmap, const FilterArgs& fa, int grid, cudaStream_t stream) {
-  size_t smem = 1024 + (size_t)TF_STAGES * TF_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 + (size_t)2 * TF_BN * 4 +
-                (size_t)(2 * TF_STAGES + 5) * 8 + 16;
-  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tensor_filter_kernel<KP, NBUF, DBG><<<grid, TF_THREADS, smem, stream>>>(tmap, fa);
+  size_t smem = 1024 + (size_t)TF_STAGES * TF_STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
+                (size_t)2 * TF_BN * 4 + (size_t)(2 * TF_STAGES + 5) * 8 + 16;
+  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, EW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tensor_filter_kernel<KP, NBUF, EW, DBG><<<grid, 64 + 128 * EW, smem, stream>>>(tmap, fa);
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -616,7 +624,11 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
   // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
   uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
-  const uint32_t n_cand = n_chunks * kprime;
+  // epilogue warps per TMEM lane quarter: the gate of a 128x128 tile costs ~1600 issue cycles with
+  // one warp per quarter; the MMA of the tile takes 4*kpad cycles
+  const uint32_t ew = (s->kpad >= 640 || dbg_scores) ? 1u : 2u;
+  const uint32_t n_lists = n_chunks * ew;  // candidate lists per query
+  const uint32_t n_cand = n_lists * kprime;
   const uint32_t n_pad = std::max(32u, next_pow2(n_cand));
   const uint32_t kpp = std::min(n_pad, std::max(32u, next_pow2(2 * k)));  // rows handed to the exact rerank
 
@@ -639,7 +651,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(scratch.alloc(&d_qstat, nq));
   SCN_TRY(scratch.alloc(&d_cscore, (size_t)nq * n_cand));
   SCN_TRY(scratch.alloc(&d_crow, (size_t)nq * n_cand));
-  SCN_TRY(scratch.alloc(&d_ctau, (size_t)nq * n_chunks));
+  SCN_TRY(scratch.alloc(&d_ctau, (size_t)nq * n_lists));
   SCN_TRY(scratch.alloc(&d_tau, nq));
   SCN_TRY(scratch.alloc(&d_rows, (size_t)nq * kpp));
   float* d_tau_chunks = nullptr;
@@ -674,14 +686,16 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   if (prof) prof->begin("tensor_filter");
   const bool two_buf = s->kpad <= 512;
   int32_t rc;
-  if (dbg_scores) rc = two_buf ? launch_filter<16, 2, true>(tmap, fa, grid, stream) : launch_filter<16, 1, true>(tmap, fa, grid, stream);
-  else if (kprime == 16) rc = two_buf ? launch_filter<16, 2, false>(tmap, fa, grid, stream) : launch_filter<16, 1, false>(tmap, fa, grid, stream);
-  else rc = two_buf ? launch_filter<32, 2, false>(tmap, fa, grid, stream) : launch_filter<32, 1, false>(tmap, fa, grid, stream);
+  if (dbg_scores) rc = two_buf ? launch_filter<16, 2, 1, true>(tmap, fa, grid, stream) : launch_filter<16, 1, 1, true>(tmap, fa, grid, stream);
+  else if (ew == 1) rc = (kprime == 16) ? launch_filter<16, 1, 1, false>(tmap, fa, grid, stream) : launch_filter<32, 1, 1, false>(tmap, fa, grid, stream);
+  else rc = (kprime == 16) ? launch_filter<16, 2, 2, false>(tmap, fa, grid, stream) : launch_filter<32, 2, 2, false>(tmap, fa, grid, stream);
   if (prof) prof->end();
   SCN_TRY(rc);
 
+  if ((size_t)n_pad * 8 > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many candidate lists (%u) for one merge block", n_lists);
+  SCN_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)n_pad * 8)));
   if (prof) prof->begin("merge_candidates");
-  merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_chunks, kprime, n_pad, kpp,
+  merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime, n_pad, kpp,
                                                                             d_rows, d_tau, d_tau_chunks);
   SCN_LAUNCHED();
   if (prof) prof->end();

@@ -121,12 +121,29 @@ def test_near_duplicates_cluster():
         assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
 
 
-def test_auto_dispatch_uses_tensor_path_for_large_batches_only():
-    db = gaussian(8192, 128, 1)
+def test_auto_dispatch():
+    # large stores: the tensor filter serves every batch size (it streams the bf16 mirror, half the
+    # bytes of the fp32 scan); small stores and dims beyond the TMEM budget use the exact scan
     s = DeviceStore(128, DistanceMetric.L2)
-    s.append(db)
-    s.search_flat(gaussian(4, 128, 2), 10)
-    assert s.last_counters()[0] == 0
+    s.append(gaussian(8192, 128, 1))
+    s.search_flat(gaussian(1, 128, 2), 10)
+    assert s.last_counters()[0] == 1
     s.search_flat(gaussian(64, 128, 2), 10)
     assert s.last_counters()[0] == 64
+    s.set_option("tensor_min_batch", 16)
+    s.search_flat(gaussian(4, 128, 2), 10)
+    assert s.last_counters()[0] == 0
+    s.close()
+    s = DeviceStore(128, DistanceMetric.L2)
+    s.append(gaussian(1000, 128, 1))
+    s.search_flat(gaussian(64, 128, 2), 10)
+    assert s.last_counters()[0] == 0
+    s.close()
+    s = DeviceStore(1536, DistanceMetric.INNER_PRODUCT)
+    db, q = gaussian(5000, 1536, 1), gaussian(20, 1536, 2)
+    s.append(db)
+    ids, dist, _ = s.search_flat(q, 10)
+    assert s.last_counters()[0] == 0
+    o = oracle.flat_search(3, db, q, 10, nthreads=8)
+    assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
     s.close()
