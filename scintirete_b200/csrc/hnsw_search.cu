@@ -46,6 +46,7 @@ struct HnswArgs {
   const uint32_t* up_off;
   uint32_t pitch, dim, n_rows;
   uint32_t s0, su;
+  uint32_t has_deleted;    // 0: no row is soft-deleted, the bitmap need not be read
   uint32_t entry_row;
   int32_t max_layer;
   const float* q;
@@ -79,11 +80,77 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t hash_size
   return false;  // table full (guarded against by the overflow check)
 }
 
-// The reference's Distance(query, row) for this lane's row, bit for bit.
+// The reference's Distance(query, row) for this lane's row, bit for bit: one lane walks one row in
+// the reference's sequential fp32 order. The row is fetched in chunks of 16 float4 that are double
+// buffered in registers, so 16-32 independent 128-bit loads per lane (up to 16 KB per warp) are in
+// flight before the first dependent add: a 512-byte row costs one memory latency instead of the
+// eight that a 4-wide unrolled loop serialises.
+constexpr int DCH = 16;  // float4 per register chunk
+
+// FULL: the chunk lies entirely inside the row -> straight-line code without predicates, so the
+// scheduler can hoist the query LDS ahead of the dependent add chain.
+template <bool FULL>
+__device__ __forceinline__ void load_chunk(float4 (&b)[DCH], const float4* __restrict__ x4, uint32_t c, uint32_t pitch4) {
+#pragma unroll
+  for (int i = 0; i < DCH; ++i) {
+    const uint32_t j = c * DCH + i;
+    if (FULL || j < pitch4) b[i] = __ldg(x4 + j);
+    else b[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // +0 terms never change the sum
+  }
+}
+
+template <int METRIC, bool FULL>
+__device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], const float4* __restrict__ q4, uint32_t c, uint32_t pitch4) {
+  float4 qa[DCH];
+#pragma unroll
+  for (int i = 0; i < DCH; ++i) {
+    const uint32_t j = c * DCH + i;
+    qa[i] = (FULL || j < pitch4) ? q4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < DCH; ++i) {
+    acc = acc_step<METRIC>(acc, qa[i].x, b[i].x);
+    acc = acc_step<METRIC>(acc, qa[i].y, b[i].y);
+    acc = acc_step<METRIC>(acc, qa[i].z, b[i].z);
+    acc = acc_step<METRIC>(acc, qa[i].w, b[i].w);
+  }
+  return acc;
+}
+
+template <int METRIC>
+__device__ __noinline__ float row_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
+                                           const float* sq, float qn, uint32_t row) {
+  const float4* x4 = reinterpret_cast<const float4*>(vec + (size_t)row * pitch);
+  const float4* q4 = reinterpret_cast<const float4*>(sq);
+  const uint32_t pitch4 = pitch >> 2;
+  const uint32_t nfull = pitch4 / DCH;          // chunks that lie entirely inside the row
+  float4 b0[DCH], b1[DCH];
+  float xn = 0.0f;
+  float acc = 0.0f;
+  if (nfull > 0) load_chunk<true>(b0, x4, 0, pitch4);
+  if (nfull > 1) load_chunk<true>(b1, x4, 1, pitch4);
+  if (METRIC == M_COS) xn = __ldg(norm + row);
+  uint32_t c = 0;
+  for (; c + 1 < nfull; c += 2) {
+    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
+    if (c + 2 < nfull) load_chunk<true>(b0, x4, c + 2, pitch4);
+    acc = acc_chunk<METRIC, true>(acc, b1, q4, c + 1, pitch4);
+    if (c + 3 < nfull) load_chunk<true>(b1, x4, c + 3, pitch4);
+  }
+  if (c < nfull) {  // odd number of full chunks: the last one sits in b0
+    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
+    ++c;
+  }
+  if (c * DCH < pitch4) {  // ragged tail (< 16 float4)
+    load_chunk<false>(b1, x4, c, pitch4);
+    acc = acc_chunk<METRIC, false>(acc, b1, q4, c, pitch4);
+  }
+  return finish_distance<METRIC>(acc, qn, xn);
+}
+
 template <int METRIC>
 __device__ __forceinline__ float lane_distance(const HnswArgs& a, const float* sq, float qn, uint32_t row) {
-  float acc = exact_acc_thread<METRIC>(sq, a.vec + (size_t)row * a.pitch, a.pitch >> 2);
-  return finish_distance<METRIC>(acc, qn, METRIC == M_COS ? __ldg(a.norm + row) : 0.0f);
+  return row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, row);
 }
 
 template <int METRIC, bool USE_GLOBAL>
@@ -142,7 +209,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
           uint32_t best_row = cur;
           for (uint32_t c0 = 0; c0 < a.su; c0 += 32) {
             uint32_t nb = (c0 + lane < a.su) ? __ldg(list + c0 + lane) : ROW_NONE;
-            bool ok = (nb != ROW_NONE) && !bit_test(a.deleted, nb);
+            bool ok = (nb != ROW_NONE) && !(a.has_deleted && bit_test(a.deleted, nb));
             float d = INF;
             if (ok) d = lane_distance<METRIC>(a, sq, qn, nb);
             evals += __popc(__ballot_sync(0xffffffffu, ok));
@@ -205,7 +272,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
           bool ok = (nb != ROW_NONE);
           // reference order: visited? -> deleted? -> mark visited. A deleted row is never
           // inserted, so testing `deleted` first and inserting only live rows is equivalent.
-          if (ok) ok = !bit_test(a.deleted, nb);
+          if (ok && a.has_deleted) ok = !bit_test(a.deleted, nb);
           if (ok) ok = visited_insert(hash, a.hash_size, nb);
           const uint32_t mask = __ballot_sync(0xffffffffu, ok);
           const uint32_t ns = __popc(mask);
@@ -222,57 +289,43 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
           if (in && cnt >= ef) in = od < (uint32_t)(wkey[ef - 1] >> 32);
           // stable admission order = adjacency order
           const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-          uint64_t key = in ? (((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1)) : KEY_NONE;
-          uint32_t row = nb;
+          const uint64_t key = ((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1);
           seq += ns;
-          const uint32_t nn = __popc(__ballot_sync(0xffffffffu, in));
+          const uint32_t mask_in = __ballot_sync(0xffffffffu, in);
+          const uint32_t nn = __popc(mask_in);
           if (!nn) continue;
-          // ---- warp bitonic sort of the new keys (ascending; KEY_NONE sinks to the end) ----
-#pragma unroll
-          for (int ks = 2; ks <= 32; ks <<= 1) {
-#pragma unroll
-            for (int j = ks >> 1; j > 0; j >>= 1) {
-              const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
-              const uint32_t orw = __shfl_xor_sync(0xffffffffu, row, j);
-              const bool up = ((lane & ks) == 0);
-              const bool lower = ((lane & j) == 0);
-              const bool take = (lower == up) ? (other < key) : (other > key);
-              if (take) {
-                key = other;
-                row = orw;
-              }
-            }
-          }
-          snk[lane] = key;
-          snr[lane] = row;
+          // ---- merge of W[0..cnt) with the nn admitted keys into the other buffer, by rank --------
+          // (keys are unique: the admission sequence number breaks distance ties in the reference's
+          // stable order.) Once W is full only a handful of neighbours pass the W[ef-1] test, so the
+          // admitted keys are simply compacted in adjacency order and every entry counts the admitted
+          // keys below it: old entry i moves to i + #{new < it}; a new entry moves to
+          // #{old < it} + #{new < it}.
+          const uint32_t slot = __popc(mask_in & ((1u << lane) - 1u));
+          if (in) snk[slot] = key;
           __syncwarp();
-          // ---- rank-based merge of W[0..cnt) and snk[0..nn) into the other buffer ----------
-          // old entry i moves to i + #{new < it}; new entry j moves to j + #{old < it}
           for (uint32_t i = lane; i < cnt; i += 32) {
             const uint64_t kv = wkey[i];
-            uint32_t lo = 0, hi = nn;
-            while (lo < hi) {
-              uint32_t mid = (lo + hi) >> 1;
-              if (snk[mid] < kv) lo = mid + 1;
-              else hi = mid;
-            }
-            const uint32_t pos = i + lo;
+            uint32_t below = 0;
+            for (uint32_t j = 0; j < nn; ++j) below += (snk[j] < kv) ? 1u : 0u;
+            const uint32_t pos = i + below;
             if (pos < ef) {
               okey[pos] = kv;
               orow[pos] = wrow[i];
             }
           }
-          if ((uint32_t)lane < nn) {
+          if (in) {
             uint32_t lo = 0, hi = cnt;
             while (lo < hi) {
               uint32_t mid = (lo + hi) >> 1;
               if (wkey[mid] < key) lo = mid + 1;
               else hi = mid;
             }
-            const uint32_t pos = lane + lo;
+            uint32_t below = 0;
+            for (uint32_t j = 0; j < nn; ++j) below += (snk[j] < key) ? 1u : 0u;
+            const uint32_t pos = lo + below;
             if (pos < ef) {
               okey[pos] = key;
-              orow[pos] = row;
+              orow[pos] = nb;
             }
           }
           cnt = min(ef, cnt + nn);
@@ -372,6 +425,7 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.n_rows = (uint32_t)s->rows;
   a.s0 = 2 * (uint32_t)s->m;
   a.su = (uint32_t)s->m;
+  a.has_deleted = (s->live != s->rows) ? 1u : 0u;
   a.entry_row = s->entry_row;
   a.max_layer = s->max_layer;
   a.q = d_q;
