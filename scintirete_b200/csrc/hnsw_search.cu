@@ -68,14 +68,40 @@ __host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pa
   return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + (global_hash ? 0 : (size_t)hash_size * 4);
 }
 
-__device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t hash_size, uint32_t row) {
-  uint32_t h = __umulhi(row * 2654435761u, hash_size);
+// visited set: open addressing over groups of four 32-bit slots (one 128-bit load per probe). Slots
+// of a group fill in order and are never emptied within a query, so a group that still has an
+// empty slot and does not hold the key proves the key absent. Returns true if `row` was inserted
+// (first visit), false if it was already there.
+template <bool GLOBAL>
+__device__ __forceinline__ uint4 ld_group(const uint32_t* p) {
+  uint4 v;
+  if (GLOBAL) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  } else {
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  }
+  return v;
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups, uint32_t row) {
+  uint32_t g = __umulhi(row * 2654435761u, n_groups);
   const uint32_t key = row + 1;
-  for (uint32_t probes = 0; probes < hash_size; ++probes) {
-    uint32_t old = atomicCAS(tab + h, HASH_EMPTY, key);
-    if (old == HASH_EMPTY) return true;
-    if (old == key) return false;
-    if (++h == hash_size) h = 0;
+  for (uint32_t probes = 0; probes <= n_groups;) {
+    uint32_t* grp = tab + g * 4;
+    const uint4 v = ld_group<GLOBAL>(grp);
+    if (v.x == key || v.y == key || v.z == key || v.w == key) return false;
+    const int e = (v.x == HASH_EMPTY) ? 0 : (v.y == HASH_EMPTY) ? 1 : (v.z == HASH_EMPTY) ? 2 : (v.w == HASH_EMPTY) ? 3 : -1;
+    if (e >= 0) {
+      const uint32_t old = atomicCAS(grp + e, HASH_EMPTY, key);
+      if (old == HASH_EMPTY) return true;
+      if (old == key) return false;
+      continue;  // another lane took the slot: look at the same group again
+    }
+    ++probes;
+    if (++g == n_groups) g = 0;
   }
   return false;  // table full (guarded against by the overflow check)
 }
@@ -87,15 +113,28 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t hash_size
 // eight that a 4-wide unrolled loop serialises.
 constexpr int DCH = 16;  // float4 per register chunk
 
+// 256-bit read-only load (rows are 32-byte aligned: pitch is a multiple of 8 floats). One lane
+// reads one row, so a warp-wide load touches up to 32 different lines and L1 spends a tag cycle on
+// each: the wider load halves the requests and touches every 32-byte sector once instead of twice.
+// (ptxas 12.9 crashes on LDG.256 inside a __noinline__ function, hence the single inlined call site.)
+struct __align__(32) F8 {
+  float4 a, b;
+};
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+  const F8 v = *reinterpret_cast<const F8*>(p);
+  a = v.a;
+  b = v.b;
+}
+
 // FULL: the chunk lies entirely inside the row -> straight-line code without predicates, so the
 // scheduler can hoist the query LDS ahead of the dependent add chain.
 template <bool FULL>
 __device__ __forceinline__ void load_chunk(float4 (&b)[DCH], const float4* __restrict__ x4, uint32_t c, uint32_t pitch4) {
 #pragma unroll
-  for (int i = 0; i < DCH; ++i) {
+  for (int i = 0; i < DCH; i += 2) {
     const uint32_t j = c * DCH + i;
-    if (FULL || j < pitch4) b[i] = __ldg(x4 + j);
-    else b[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // +0 terms never change the sum
+    if (FULL || j < pitch4) ldg256(x4 + j, b[i], b[i + 1]);  // pitch4 is even
+    else b[i] = b[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);  // +0 terms never change the sum
   }
 }
 
@@ -118,7 +157,7 @@ __device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], co
 }
 
 template <int METRIC>
-__device__ __noinline__ float row_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
+__device__ __forceinline__ float row_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
                                            const float* sq, float qn, uint32_t row) {
   const float4* x4 = reinterpret_cast<const float4*>(vec + (size_t)row * pitch);
   const float4* q4 = reinterpret_cast<const float4*>(sq);
@@ -148,11 +187,6 @@ __device__ __noinline__ float row_distance(const float* __restrict__ vec, const 
   return finish_distance<METRIC>(acc, qn, xn);
 }
 
-template <int METRIC>
-__device__ __forceinline__ float lane_distance(const HnswArgs& a, const float* sq, float qn, uint32_t row) {
-  return row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, row);
-}
-
 template <int METRIC, bool USE_GLOBAL>
 __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
   extern __shared__ __align__(16) unsigned char smem_hnsw[];
@@ -169,6 +203,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
   uint32_t* snr = wrow1 + a.ef_pad;                              // rows of the sorted new keys
   uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : (snr + 32);
   const uint32_t ef = a.ef;
+  const uint32_t n_groups = a.hash_size >> 2;  // hash_size is a multiple of 4
   const uint32_t nq = a.qlist ? min(*a.nq_dev, a.nq) : a.nq;
   const float INF = __int_as_float(0x7f800000);
   unsigned long long evals = 0, hops = 0;
@@ -177,7 +212,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
     const uint32_t qi = a.qlist ? a.qlist[qslot] : qslot;
     __syncwarp();
     for (uint32_t i = lane; i < a.pitch; i += 32) sq[i] = (i < a.dim) ? a.q[(size_t)qi * a.dim + i] : 0.0f;
-    for (uint32_t i = lane; i < a.hash_size; i += 32) hash[i] = HASH_EMPTY;
+    for (uint32_t i = lane; i < n_groups; i += 32) reinterpret_cast<uint4*>(hash)[i] = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
     __syncwarp();
     float qn = 0.0f;
     if (METRIC == M_COS) {
@@ -194,149 +229,244 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
     uint32_t cur = a.entry_row;
     const bool have_entry = (cur != ROW_NONE) && (cur < a.n_rows) && !bit_test(a.deleted, cur) && a.max_layer >= 0;
     if (have_entry) {
-      // ---- entry distance -------------------------------------------------------------------
+      // The three phases of HNSW.Search (entry distance, greedy descent, layer-0 beam) run through
+      // ONE loop: produce a batch of up to 32 rows (one per lane) -> evaluate it -> consume the
+      // distances. The distance code (128 registers of row data in flight) is thus instantiated
+      // once. All state below is warp-uniform.
+      enum { PH_ENTRY = 0, PH_DESCENT = 1, PH_BEAM = 2 };
+      int phase = PH_ENTRY;
+      int layer = a.max_layer;
+      bool in_list = false;            // an adjacency list is being walked (chunk c0 of list_len)
+      const uint32_t* list = nullptr;
+      uint32_t list_len = 0, c0 = 0;
       float dcur = 0.0f;
-      if (lane == 0) dcur = lane_distance<METRIC>(a, sq, qn, cur);
-      dcur = __shfl_sync(0xffffffffu, dcur, 0);
-      ++evals;
-      // ---- greedy descent, layers maxLayer..1 with numClosest = 1 (hnsw.go:309-311) -----------
-      for (int layer = a.max_layer; layer >= 1; --layer) {
-        for (;;) {
-          if ((int)a.levels[cur] < layer) break;  // GetConnections(layer) is empty (hnsw.go:45-50)
-          ++hops;
-          const uint32_t* list = a.adj_up + ((size_t)a.up_off[cur] + (layer - 1)) * a.su;
-          float best = dcur;
-          uint32_t best_row = cur;
-          for (uint32_t c0 = 0; c0 < a.su; c0 += 32) {
-            uint32_t nb = (c0 + lane < a.su) ? __ldg(list + c0 + lane) : ROW_NONE;
-            bool ok = (nb != ROW_NONE) && !(a.has_deleted && bit_test(a.deleted, nb));
-            float d = INF;
-            if (ok) d = lane_distance<METRIC>(a, sq, qn, nb);
-            evals += __popc(__ballot_sync(0xffffffffu, ok));
-            // first strict minimum in list order (the reference's sequential `d < W[0].d` updates)
-            float dm = (ok && d == d) ? d : INF;
-            uint32_t im = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              float od = __shfl_xor_sync(0xffffffffu, dm, o);
-              uint32_t oi = __shfl_xor_sync(0xffffffffu, im, o);
-              if (od < dm || (od == dm && oi < im)) {
-                dm = od;
-                im = oi;
-              }
-            }
-            if (dm < best) {
-              best = dm;
-              best_row = __shfl_sync(0xffffffffu, nb, im);
-            }
-          }
-          if (best_row == cur) break;
-          cur = best_row;
-          dcur = best;
-        }
-      }
-      // ---- layer 0 beam (hnsw.go:314, 487-557) ---------------------------------------------
-      uint32_t seq = 1, visited = 1;
-      if (lane == 0) {
-        wkey[0] = ((uint64_t)f32_ord(dcur) << 32);
-        wrow[0] = cur;
-      }
-      cnt = 1;
-      visited_insert(hash, a.hash_size, cur);
-      __syncwarp();
+      float best = 0.0f;               // descent: closest neighbour so far of the expanded node
+      uint32_t best_row = cur;
+      uint32_t seq = 1, visited = 1;   // beam: admission sequence, size of the visited set
+      uint32_t p_lo = 0;               // beam: every entry of W before p_lo has been expanded
+      uint32_t pre_row = ROW_NONE;     // beam: adjacency prefetched for this row (the runner-up)
+      uint32_t pre_nb = ROW_NONE;
       for (;;) {
-        // closest un-expanded entry of W
-        int p = -1;
-        for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
-          uint32_t i = b0 + lane;
-          bool un = (i < cnt) && !(wkey[i] & 1ull);
-          uint32_t m = __ballot_sync(0xffffffffu, un);
-          if (m) {
-            p = (int)b0 + __ffs(m) - 1;
+        // ================= produce: the next non-empty batch of rows, or the end =================
+        uint32_t nb = ROW_NONE;
+        bool ok = false;
+        uint32_t mask = 0;
+        bool finished = false;
+        for (;;) {
+          if (phase == PH_ENTRY) {
+            nb = cur;
+            ok = (lane == 0);
+            mask = 1u;
             break;
           }
-        }
-        if (p < 0) break;
-        cur = wrow[p];
-        __syncwarp();
-        if (lane == 0) wkey[p] |= 1ull;
-        __syncwarp();
-        ++hops;
-        if (visited + a.s0 > a.hash_size - (a.hash_size >> 3)) {  // keep the table below 7/8 full
-          overflow = true;
-          break;
-        }
-        const uint32_t* list = a.adj0 + (size_t)cur * a.s0;
-        for (uint32_t c0 = 0; c0 < a.s0; c0 += 32) {
-          uint32_t nb = (c0 + lane < a.s0) ? __ldg(list + c0 + lane) : ROW_NONE;
-          bool ok = (nb != ROW_NONE);
+          if (phase == PH_DESCENT) {
+            // greedy descent, layers maxLayer..1 with numClosest = 1 (hnsw.go:309-311)
+            if (!in_list) {
+              if (layer < 1) {
+                // ---- layer 0 beam starts from the descent's result (hnsw.go:314) ----
+                phase = PH_BEAM;
+                if (lane == 0) {
+                  wkey[0] = ((uint64_t)f32_ord(dcur) << 32);
+                  wrow[0] = cur;
+                }
+                cnt = 1;
+                visited_insert<USE_GLOBAL>(hash, n_groups, cur);
+                __syncwarp();
+                continue;
+              }
+              ++hops;
+              if ((int)a.levels[cur] < layer) {  // GetConnections(layer) is empty (hnsw.go:45-50)
+                --layer;
+                continue;
+              }
+              list = a.adj_up + ((size_t)a.up_off[cur] + (layer - 1)) * a.su;
+              list_len = a.su;
+              c0 = 0;
+              in_list = true;
+              best = dcur;
+              best_row = cur;
+            }
+            nb = (c0 + lane < list_len) ? __ldg(list + c0 + lane) : ROW_NONE;
+            ok = (nb != ROW_NONE) && !(a.has_deleted && bit_test(a.deleted, nb));
+            mask = __ballot_sync(0xffffffffu, ok);
+            evals += __popc(mask);
+            break;
+          }
+          // ---- PH_BEAM (searchLayer on layer 0, hnsw.go:487-557) ----
+          if (!in_list) {
+            // closest un-expanded entry of W (== pop of the reference's `dynamic` list)
+            uint32_t m = 0, b0 = p_lo & ~31u;
+            for (; b0 < cnt; b0 += 32) {
+              const uint32_t i = b0 + lane;
+              const bool un = (i < cnt) && !(reinterpret_cast<const uint32_t*>(wkey)[2 * i] & 1u);
+              m = __ballot_sync(0xffffffffu, un);
+              if (m) break;
+            }
+            if (!m) {
+              finished = true;
+              break;
+            }
+            const uint32_t p = b0 + __ffs(m) - 1;
+            p_lo = p + 1;
+            cur = wrow[p];
+            // the runner-up is the most likely next expansion: fetch its adjacency line now, so
+            // that the adjacency -> rows dependency of the next hop starts from registers
+            const uint32_t m2 = m & (m - 1);
+            const uint32_t row2 = m2 ? wrow[b0 + __ffs(m2) - 1] : ROW_NONE;
+            __syncwarp();
+            if (lane == 0) reinterpret_cast<uint32_t*>(wkey)[2 * p] |= 1u;
+            __syncwarp();
+            ++hops;
+            if (visited + a.s0 > a.hash_size - (a.hash_size >> 3)) {  // keep the table below 7/8 full
+              overflow = true;
+              finished = true;
+              break;
+            }
+            list = a.adj0 + (size_t)cur * a.s0;
+            list_len = a.s0;
+            c0 = 0;
+            in_list = true;
+            if (cur == pre_row) nb = pre_nb;
+            else nb = ((uint32_t)lane < list_len) ? __ldg(list + lane) : ROW_NONE;
+            pre_row = row2;
+            if (row2 != ROW_NONE && (uint32_t)lane < list_len) pre_nb = __ldg(a.adj0 + (size_t)row2 * a.s0 + lane);
+          } else {
+            nb = (c0 + lane < list_len) ? __ldg(list + c0 + lane) : ROW_NONE;
+          }
+          ok = (nb != ROW_NONE);
           // reference order: visited? -> deleted? -> mark visited. A deleted row is never
           // inserted, so testing `deleted` first and inserting only live rows is equivalent.
           if (ok && a.has_deleted) ok = !bit_test(a.deleted, nb);
-          if (ok) ok = visited_insert(hash, a.hash_size, nb);
-          const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+          if (ok) ok = visited_insert<USE_GLOBAL>(hash, n_groups, nb);
+          mask = __ballot_sync(0xffffffffu, ok);
           const uint32_t ns = __popc(mask);
-          if (!ns) continue;
+          if (!ns) {  // nothing new in this chunk
+            c0 += 32;
+            if (c0 >= list_len) in_list = false;
+            continue;
+          }
           visited += ns;
           evals += ns;
-          float d = INF;
-          if (ok) d = lane_distance<METRIC>(a, sq, qn, nb);
-          // admission (hnsw.go:536-542): while |W| < ef everything enters; once full only
-          // d < W[ef-1].d (strict; a NaN never passes). Entering while the list is not full and
-          // being pushed out later is the same as losing the final cut of the merge below.
-          const uint32_t od = f32_ord(d);
-          bool in = ok;
-          if (in && cnt >= ef) in = od < (uint32_t)(wkey[ef - 1] >> 32);
-          // stable admission order = adjacency order
-          const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-          const uint64_t key = ((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1);
-          seq += ns;
-          const uint32_t mask_in = __ballot_sync(0xffffffffu, in);
-          const uint32_t nn = __popc(mask_in);
-          if (!nn) continue;
-          // ---- merge of W[0..cnt) with the nn admitted keys into the other buffer, by rank --------
-          // (keys are unique: the admission sequence number breaks distance ties in the reference's
-          // stable order.) Once W is full only a handful of neighbours pass the W[ef-1] test, so the
-          // admitted keys are simply compacted in adjacency order and every entry counts the admitted
-          // keys below it: old entry i moves to i + #{new < it}; a new entry moves to
-          // #{old < it} + #{new < it}.
-          const uint32_t slot = __popc(mask_in & ((1u << lane) - 1u));
-          if (in) snk[slot] = key;
-          __syncwarp();
-          for (uint32_t i = lane; i < cnt; i += 32) {
-            const uint64_t kv = wkey[i];
-            uint32_t below = 0;
-            for (uint32_t j = 0; j < nn; ++j) below += (snk[j] < kv) ? 1u : 0u;
-            const uint32_t pos = i + below;
-            if (pos < ef) {
-              okey[pos] = kv;
-              orow[pos] = wrow[i];
-            }
-          }
-          if (in) {
-            uint32_t lo = 0, hi = cnt;
-            while (lo < hi) {
-              uint32_t mid = (lo + hi) >> 1;
-              if (wkey[mid] < key) lo = mid + 1;
-              else hi = mid;
-            }
-            uint32_t below = 0;
-            for (uint32_t j = 0; j < nn; ++j) below += (snk[j] < key) ? 1u : 0u;
-            const uint32_t pos = lo + below;
-            if (pos < ef) {
-              okey[pos] = key;
-              orow[pos] = nb;
-            }
-          }
-          cnt = min(ef, cnt + nn);
-          __syncwarp();
-          uint64_t* tk = wkey;
-          wkey = okey;
-          okey = tk;
-          uint32_t* tr = wrow;
-          wrow = orow;
-          orow = tr;
+          break;
         }
+        if (finished) break;
+
+        // ================= evaluate: the reference's Distance(), one row per lane ================
+        float d = INF;
+        if (ok) d = row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb);
+
+        // ================= consume ==============================================================
+        if (phase == PH_ENTRY) {
+          dcur = __shfl_sync(0xffffffffu, d, 0);
+          ++evals;
+          phase = PH_DESCENT;
+          continue;
+        }
+        if (phase == PH_DESCENT) {
+          // first strict minimum in list order (the reference's sequential `d < W[0].d` updates)
+          float dm = (ok && d == d) ? d : INF;
+          uint32_t im = lane;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, dm, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, im, o);
+            if (od < dm || (od == dm && oi < im)) {
+              dm = od;
+              im = oi;
+            }
+          }
+          if (dm < best) {
+            best = dm;
+            best_row = __shfl_sync(0xffffffffu, nb, im);
+          }
+          c0 += 32;
+          if (c0 >= list_len) {
+            in_list = false;
+            if (best_row == cur) --layer;  // no closer neighbour: this layer is done
+            else {
+              cur = best_row;
+              dcur = best;
+            }
+          }
+          continue;
+        }
+        // ---- PH_BEAM: admission (hnsw.go:536-542): while |W| < ef everything enters; once full only
+        // d < W[ef-1].d (strict; a NaN never passes). Entering while the list is not full and
+        // being pushed out later is the same as losing the final cut of the merge below.
+        c0 += 32;
+        if (c0 >= list_len) in_list = false;
+        const uint32_t od = f32_ord(d);
+        bool in = ok;
+        if (in && cnt >= ef) in = od < reinterpret_cast<const uint32_t*>(wkey)[2 * (ef - 1) + 1];
+        // stable admission order = adjacency order
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+        const uint64_t key = ((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1);
+        seq += __popc(mask);
+        const uint32_t mask_in = __ballot_sync(0xffffffffu, in);
+        const uint32_t nn = __popc(mask_in);
+        if (!nn) continue;
+        // ---- merge of W[0..cnt) with the nn admitted keys into the other buffer, by rank ----------
+        // (keys are unique: the admission sequence number breaks distance ties in the reference's
+        // stable order.) Once W is full only a handful of neighbours pass the W[ef-1] test, so the
+        // admitted keys are compacted in adjacency order (lane j < nn then owns new entry j) and
+        // every entry counts the keys of the other list below it: old entry i moves to
+        // i + #{new < it}; new entry j moves to #{old < it} + #{new < it}.
+        const uint32_t slot = __popc(mask_in & ((1u << lane) - 1u));
+        if (in) {
+          snk[slot] = key;
+          snr[slot] = nb;
+        }
+        __syncwarp();
+        const bool mine = (uint32_t)lane < nn;
+        const uint64_t nkey = mine ? snk[lane] : KEY_NONE;
+        uint32_t npos = 0;  // #{old < nkey} + #{new < nkey}
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
+          uint64_t kv[4];
+          uint32_t rw[4], below[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * 32 + lane;
+            kv[u] = (i < cnt) ? wkey[i] : KEY_NONE;
+            rw[u] = (i < cnt) ? wrow[i] : ROW_NONE;
+            below[u] = 0;
+          }
+          for (uint32_t j = 0; j < nn; ++j) {
+            const uint64_t nk = snk[j];  // broadcast
+            uint32_t c = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool lt = nk < kv[u];
+              below[u] += lt ? 1u : 0u;
+              c += (!lt && kv[u] != KEY_NONE) ? 1u : 0u;  // old key below new key j (keys are distinct)
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            if ((uint32_t)lane == j) npos += c;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * 32 + lane;
+            const uint32_t pos = i + below[u];
+            if (i < cnt && pos < ef) {
+              okey[pos] = kv[u];
+              orow[pos] = rw[u];
+            }
+          }
+        }
+        for (uint32_t j = 0; j < nn; ++j) npos += (snk[j] < nkey) ? 1u : 0u;
+        if (mine && npos < ef) {
+          okey[npos] = nkey;
+          orow[npos] = snr[lane];
+        }
+        // a new (un-expanded) entry may have landed in front of p_lo
+        p_lo = min(p_lo, __reduce_min_sync(0xffffffffu, mine ? npos : 0xFFFFFFFFu));
+        cnt = min(ef, cnt + nn);
+        __syncwarp();
+        uint64_t* tk = wkey;
+        wkey = okey;
+        okey = tk;
+        uint32_t* tr = wrow;
+        wrow = orow;
+        orow = tr;
       }
     }
 

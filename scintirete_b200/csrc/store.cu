@@ -206,7 +206,7 @@ int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store
   scn_store* s = new scn_store();
   s->device = device;
   s->dim = dim;
-  s->pitch = round_up(dim, 4);
+  s->pitch = round_up(dim, 8);  // rows 32-byte aligned (256-bit loads in hnsw_search)
   s->kpad = round_up(dim, 64);
   s->metric = metric;
   if (cudaMalloc(&s->d_bounds, 4 * sizeof(float)) != cudaSuccess) {

@@ -1,7 +1,7 @@
 // store.h — device-memory mirror of the reference's node store (hnsw.go:17-26, 115) on one GPU.
 //
 // HBM layout (rows in insertion order; row == id-1 for auto-assigned ids, collection.go:115-116):
-//   vec      float   [cap][pitch]     fp32 rows, pitch = dim rounded up to 4 floats, zero padded
+//   vec      float   [cap][pitch]     fp32 rows, pitch = dim rounded up to 8 floats, zero padded
 //   norm     float   [cap]            ||x|| in the reference's sequential fp32 order (cosine normB)
 //   mirror   bf16    [cap][kpad]      tensor-core operand: bf16(x) (L2, IP) or bf16(x/||x||) (cosine),
 //                                     kpad = dim rounded up to 64, zero padded

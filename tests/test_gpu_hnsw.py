@@ -112,3 +112,23 @@ def test_visited_overflow_path_gives_same_answer():
     o_ids, _, o_cnt, _ = h.search_batch(q, 10, 16, nthreads=4)
     ids, _, cnt = g.search_batch(q, SearchParams(top_k=10, ef_search=16))
     assert np.array_equal(cnt, o_cnt) and recall(ids, o_ids) >= 0.99
+
+
+@pytest.mark.parametrize("metric,d", [(DistanceMetric.L2, 128), (DistanceMetric.COSINE, 96), (DistanceMetric.INNER_PRODUCT, 40)])
+def test_walk_is_identical_to_the_reference_walk(metric, d):
+    # Stronger than the recall bar: traversal distances are accumulated in the reference's order
+    # and admissions follow its stable (distance, admission) order, so on data without exact
+    # float ties the GPU returns the very same ids, in the same order, with the same distance bits
+    # as hnsw.go:292-350 restated by the oracle, after the same number of expansions.
+    n, nq, k, ef = 6000, 300, 10, 64
+    db, h, g = _pair(metric, n, d)
+    q = gaussian(nq, d, 99)
+    o_ids, o_dist, o_cnt, o_stats = h.search_batch(q, k, ef, nthreads=8)
+    g.store.set_option("profile", 1)
+    ids, dist, cnt = g.search_batch(q, SearchParams(top_k=k, ef_search=ef))
+    counters = g.store.last_counters()
+    g.store.set_option("profile", 0)
+    assert np.array_equal(cnt, o_cnt)
+    assert np.array_equal(ids, o_ids)
+    assert np.array_equal(dist, o_dist)
+    assert counters[1] == o_stats[1], (counters, o_stats)   # expansions, all layers
