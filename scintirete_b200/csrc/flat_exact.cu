@@ -381,8 +381,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ v
       if (c < ncand) {
         uint32_t row = cand[(size_t)qi * ncand + c];
         if (row < n_rows && !bit_test(deleted, row)) {
-          float acc = exact_acc_thread<METRIC>(s_q, vec + (size_t)row * pitch, pitch / 4);
-          float d = finish_distance<METRIC>(acc, METRIC == M_COS ? s_qnorm : 0.0f, METRIC == M_COS ? __ldg(norm + row) : 0.0f);
+          const float d = row_distance<METRIC>(vec, norm, pitch, s_q, METRIC == M_COS ? s_qnorm : 0.0f, row);
           key = make_key(d, row + row_base);
         }
       }

@@ -27,7 +27,8 @@ namespace scn {
 constexpr int TF_BM = 128;        // queries per CTA (UMMA M)
 constexpr int TF_BK = 64;         // bf16 per smem K block = one 128-byte swizzle row
 constexpr int TF_THREADS = 192;   // warp 0: TMA, warp 1: MMA, warps 2..: epilogue, 4*EW warps (TMEM lane quarters 2,3,0,1,...)
-constexpr int TF_MAX_KPAD = 768;  // A operand must fit TMEM next to the accumulators
+constexpr int TF_MAX_KPAD = 768;  // widest A operand that fits TMEM next to an accumulator (TMEM-stationary queries)
+constexpr int TF_MAX_KPAD_STREAM = 8192;  // beyond 768 the query block is streamed through shared memory with the rows
 
 // ---- PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +72,15 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T (both operands K-major 128B-swizzled tiles)
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -124,15 +134,28 @@ struct FilterArgs {
 };
 
 constexpr int TF_BN = 128;                        // database rows per tile (UMMA N)
-constexpr int TF_STAGE_BYTES = TF_BN * TF_BK * 2;  // 16 KB
-constexpr int TF_STAGES = 10;
 
 // KP   : candidates kept per (query, chunk, column slice); scores live in registers, rows in smem
 // NBUF : accumulator buffers in TMEM (2 when the A operand leaves room, else 1)
 // EW   : epilogue warps per TMEM lane quarter; each owns a slice of 128/EW columns of every tile.
 //        Short K (small dim) makes the MMA of a tile cheaper than its gate, so more warps gate.
-template <int KP, int NBUF, int EW, bool DBG>
-__global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
+// ASM  : kpad > 768: a 128-query block no longer fits TMEM next to an accumulator, so the A operand
+//        is streamed by TMA with the rows (one 16 KB A block + one 16 KB B block per stage, both
+//        128B-swizzled K-major) and the MMAs take both operands from shared memory. The smem fill
+//        rate this needs (128 B/clk at full tensor rate) is about twice what an SM gets from L2,
+//        so this variant is L2-bandwidth-bound at roughly half the tensor roofline.
+template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+struct FilterCfg {
+  static constexpr int STAGE_BYTES = ASM ? 2 * (TF_BM * TF_BK * 2) : (TF_BM * TF_BK * 2);
+  static constexpr int STAGES = ASM ? (KP > 16 ? 5 : 6) : 10;
+};
+
+template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
+    tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a, FilterArgs a) {
+  constexpr int TF_STAGES = FilterCfg<KP, NBUF, EW, DBG, ASM>::STAGES;
+  constexpr int TF_STAGE_BYTES = FilterCfg<KP, NBUF, EW, DBG, ASM>::STAGE_BYTES;
+  constexpr int TF_B_OFF = ASM ? (TF_BM * TF_BK * 2) : 0;  // B block within a stage (A block first when streamed)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve-up: [B stages][cand_row 128*EW*KP][queue 2*16*128*EW][aux 2*BN][barriers][tmem ptr]
   // 1024-byte alignment for the 128B-swizzled tiles; plain pointer arithmetic on the __shared__
@@ -184,6 +207,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const _
     uint32_t stage = 0, phase = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / a.n_qblocks;
+      const uint32_t qblk = item - chunk * a.n_qblocks;
       const uint32_t t0 = chunk * a.tiles_per_chunk;
       const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
       for (uint32_t t = t0; t < t1; ++t) {
@@ -191,7 +215,8 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const _
           mbar_wait(empty + stage, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(full + stage, TF_STAGE_BYTES);
-            tma_load_2d(sb + stage * TF_STAGE_BYTES, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * TF_BN));
+            if (ASM) tma_load_2d(sb + stage * TF_STAGE_BYTES, &tmap_a, full + stage, (int)(kb * TF_BK), (int)(qblk * TF_BM));
+            tma_load_2d(sb + stage * TF_STAGE_BYTES + TF_B_OFF, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * TF_BN));
           }
           __syncwarp();
           if (++stage == TF_STAGES) {
@@ -211,9 +236,11 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const _
       const uint32_t chunk = item / a.n_qblocks;
       const uint32_t t0 = chunk * a.tiles_per_chunk;
       const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-      mbar_wait(a_ready, a_phase);
-      a_phase ^= 1;
-      tc_fence_after();
+      if (!ASM) {
+        mbar_wait(a_ready, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+      }
       for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
         const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
         const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
@@ -224,12 +251,15 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const _
           mbar_wait(full + stage, phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
+            const uint64_t adesc = bdesc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
+            const uint64_t bdesc = adesc + (uint64_t)(TF_B_OFF >> 4);
             const uint32_t a_col = tmem_a + kb * (TF_BK / 2);
 #pragma unroll
             for (uint32_t k = 0; k < TF_BK / 16; ++k) {
-              // A: 16 bf16 of K = 8 TMEM columns; B: 32 bytes further along the swizzled row
-              tc_mma_ts(d_tmem, a_col + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              // A: 16 bf16 of K = 8 TMEM columns (or 32 bytes along the swizzled smem row);
+              // B: 32 bytes further along the swizzled row
+              if (ASM) tc_mma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              else tc_mma_ts(d_tmem, a_col + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
             }
             tc_commit(empty + stage);                     // smem slot free once these MMAs retire
             if (kb == KB - 1) tc_commit(acc_full + buf);  // accumulator ready for the epilogue
@@ -262,7 +292,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1) tensor_filter_kernel(const _
       const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
       const uint32_t q_global = qblk * TF_BM + qrow;
       // ---- A operand: this thread's query row -> its TMEM lane, packed bf16 pairs ----
-      {
+      if (!ASM) {
         const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)q_global * a.kpad);
         const uint32_t n16 = a.kpad / 8;  // 16-byte groups = 4 TMEM columns each
         for (uint32_t i = slice; i < n16; i += EW) {  // the EW warps of a quarter share the copy
@@ -580,7 +610,7 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool tensor_path_supported(const scn_store* s, uint32_t k) { return s->kpad <= TF_MAX_KPAD && k <= 24 && s->rows >= 1; }
+bool tensor_path_supported(const scn_store* s, uint32_t k) { return s->kpad <= TF_MAX_KPAD_STREAM && k <= 24 && s->rows >= 1; }
 
 static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   uint32_t cmax = std::max(1u, std::min(256u, n_tiles / 8));
@@ -598,12 +628,13 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   return 1;
 }
 
-template <int KP, int NBUF, int EW, bool DBG>
-static int32_t launch_filter(const CUtensorMap& tmap, const FilterArgs& fa, int grid, cudaStream_t stream) {
-  size_t smem = 1024 + (size_t)TF_STAGES * TF_STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
-                (size_t)2 * TF_BN * 4 + (size_t)(2 * TF_STAGES + 5) * 8 + 16;
-  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, EW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tensor_filter_kernel<KP, NBUF, EW, DBG><<<grid, 64 + 128 * EW, smem, stream>>>(tmap, fa);
+template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream) {
+  using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM>;
+  size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
+                (size_t)2 * TF_BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
+  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tensor_filter_kernel<KP, NBUF, EW, DBG, ASM><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -626,11 +657,17 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
   // epilogue warps per TMEM lane quarter: the gate of a 128x128 tile costs ~1600 issue cycles with
   // one warp per quarter; the MMA of the tile takes 4*kpad cycles
+  const bool stream_a = s->kpad > TF_MAX_KPAD;  // query block too wide for TMEM: stream it with the rows
   const uint32_t ew = (s->kpad >= 640 || dbg_scores) ? 1u : 2u;
   const uint32_t n_lists = n_chunks * ew;  // candidate lists per query
+  // few lists per query (huge batches) concentrate the global top-k in one list: at wide rows, where
+  // the certificate needs a bigger margin, keep 32 per list so that its threshold stays far below
+  if (stream_a && n_lists < 8 && !dbg_scores) kprime = 32u;
   const uint32_t n_cand = n_lists * kprime;
   const uint32_t n_pad = std::max(32u, next_pow2(n_cand));
-  const uint32_t kpp = std::min(n_pad, std::max(32u, next_pow2(2 * k)));  // rows handed to the exact rerank
+  // rows handed to the exact rerank. The certificate's worst-case rounding bound grows like D while
+  // the gaps between order statistics grow like sqrt(D): wide rows get a deeper cut.
+  const uint32_t kpp = std::min(n_pad, s->kpad > TF_MAX_KPAD ? std::max(64u, next_pow2(4 * k)) : std::max(32u, next_pow2(2 * k)));
 
   // B operand tensor map: mirror [rows][kpad] bf16, box {64, BN}, 128B swizzle, OOB rows read as zero
   CUtensorMap tmap;
@@ -667,6 +704,16 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_LAUNCHED();
   if (prof) prof->end();
 
+  // A operand tensor map (streamed variant only): bf16 queries [nq_pad][kpad], same tiling as the rows
+  CUtensorMap tmap_a = tmap;
+  if (stream_a) {
+    cuuint64_t adim[2] = {s->kpad, nq_pad};
+    cuuint32_t abox[2] = {TF_BK, TF_BM};
+    cr = enc(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d_qb, adim, gstr, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled (queries) failed (%d)", (int)cr);
+  }
+
   FilterArgs fa;
   fa.qb = d_qb;
   fa.aux = s->d_aux;
@@ -686,9 +733,20 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   if (prof) prof->begin("tensor_filter");
   const bool two_buf = s->kpad <= 512;
   int32_t rc;
-  if (dbg_scores) rc = two_buf ? launch_filter<16, 2, 1, true>(tmap, fa, grid, stream) : launch_filter<16, 1, 1, true>(tmap, fa, grid, stream);
-  else if (ew == 1) rc = (kprime == 16) ? launch_filter<16, 1, 1, false>(tmap, fa, grid, stream) : launch_filter<32, 1, 1, false>(tmap, fa, grid, stream);
-  else rc = (kprime == 16) ? launch_filter<16, 2, 2, false>(tmap, fa, grid, stream) : launch_filter<32, 2, 2, false>(tmap, fa, grid, stream);
+  if (stream_a) {
+    if (dbg_scores) rc = launch_filter<16, 2, 1, true, true>(tmap, tmap_a, fa, grid, stream);
+    else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true>(tmap, tmap_a, fa, grid, stream)
+                             : launch_filter<32, 2, 1, false, true>(tmap, tmap_a, fa, grid, stream);
+  } else if (dbg_scores) {
+    rc = two_buf ? launch_filter<16, 2, 1, true, false>(tmap, tmap_a, fa, grid, stream)
+                 : launch_filter<16, 1, 1, true, false>(tmap, tmap_a, fa, grid, stream);
+  } else if (ew == 1) {
+    rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false>(tmap, tmap_a, fa, grid, stream)
+                        : launch_filter<32, 1, 1, false, false>(tmap, tmap_a, fa, grid, stream);
+  } else {
+    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false>(tmap, tmap_a, fa, grid, stream)
+                        : launch_filter<32, 2, 2, false, false>(tmap, tmap_a, fa, grid, stream);
+  }
   if (prof) prof->end();
   SCN_TRY(rc);
 

@@ -106,87 +106,6 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups,
   return false;  // table full (guarded against by the overflow check)
 }
 
-// The reference's Distance(query, row) for this lane's row, bit for bit: one lane walks one row in
-// the reference's sequential fp32 order. The row is fetched in chunks of 16 float4 that are double
-// buffered in registers, so 16-32 independent 128-bit loads per lane (up to 16 KB per warp) are in
-// flight before the first dependent add: a 512-byte row costs one memory latency instead of the
-// eight that a 4-wide unrolled loop serialises.
-constexpr int DCH = 16;  // float4 per register chunk
-
-// 256-bit read-only load (rows are 32-byte aligned: pitch is a multiple of 8 floats). One lane
-// reads one row, so a warp-wide load touches up to 32 different lines and L1 spends a tag cycle on
-// each: the wider load halves the requests and touches every 32-byte sector once instead of twice.
-// (ptxas 12.9 crashes on LDG.256 inside a __noinline__ function, hence the single inlined call site.)
-struct __align__(32) F8 {
-  float4 a, b;
-};
-__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
-  const F8 v = *reinterpret_cast<const F8*>(p);
-  a = v.a;
-  b = v.b;
-}
-
-// FULL: the chunk lies entirely inside the row -> straight-line code without predicates, so the
-// scheduler can hoist the query LDS ahead of the dependent add chain.
-template <bool FULL>
-__device__ __forceinline__ void load_chunk(float4 (&b)[DCH], const float4* __restrict__ x4, uint32_t c, uint32_t pitch4) {
-#pragma unroll
-  for (int i = 0; i < DCH; i += 2) {
-    const uint32_t j = c * DCH + i;
-    if (FULL || j < pitch4) ldg256(x4 + j, b[i], b[i + 1]);  // pitch4 is even
-    else b[i] = b[i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);  // +0 terms never change the sum
-  }
-}
-
-template <int METRIC, bool FULL>
-__device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], const float4* __restrict__ q4, uint32_t c, uint32_t pitch4) {
-  float4 qa[DCH];
-#pragma unroll
-  for (int i = 0; i < DCH; ++i) {
-    const uint32_t j = c * DCH + i;
-    qa[i] = (FULL || j < pitch4) ? q4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int i = 0; i < DCH; ++i) {
-    acc = acc_step<METRIC>(acc, qa[i].x, b[i].x);
-    acc = acc_step<METRIC>(acc, qa[i].y, b[i].y);
-    acc = acc_step<METRIC>(acc, qa[i].z, b[i].z);
-    acc = acc_step<METRIC>(acc, qa[i].w, b[i].w);
-  }
-  return acc;
-}
-
-template <int METRIC>
-__device__ __forceinline__ float row_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
-                                           const float* sq, float qn, uint32_t row) {
-  const float4* x4 = reinterpret_cast<const float4*>(vec + (size_t)row * pitch);
-  const float4* q4 = reinterpret_cast<const float4*>(sq);
-  const uint32_t pitch4 = pitch >> 2;
-  const uint32_t nfull = pitch4 / DCH;          // chunks that lie entirely inside the row
-  float4 b0[DCH], b1[DCH];
-  float xn = 0.0f;
-  float acc = 0.0f;
-  if (nfull > 0) load_chunk<true>(b0, x4, 0, pitch4);
-  if (nfull > 1) load_chunk<true>(b1, x4, 1, pitch4);
-  if (METRIC == M_COS) xn = __ldg(norm + row);
-  uint32_t c = 0;
-  for (; c + 1 < nfull; c += 2) {
-    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
-    if (c + 2 < nfull) load_chunk<true>(b0, x4, c + 2, pitch4);
-    acc = acc_chunk<METRIC, true>(acc, b1, q4, c + 1, pitch4);
-    if (c + 3 < nfull) load_chunk<true>(b1, x4, c + 3, pitch4);
-  }
-  if (c < nfull) {  // odd number of full chunks: the last one sits in b0
-    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
-    ++c;
-  }
-  if (c * DCH < pitch4) {  // ragged tail (< 16 float4)
-    load_chunk<false>(b1, x4, c, pitch4);
-    acc = acc_chunk<METRIC, false>(acc, b1, q4, c, pitch4);
-  }
-  return finish_distance<METRIC>(acc, qn, xn);
-}
-
 template <int METRIC, bool USE_GLOBAL>
 __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
   extern __shared__ __align__(16) unsigned char smem_hnsw[];

@@ -32,7 +32,7 @@ def debug_scores(store, q):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("n,d,nq", [(3000, 768, 130), (2500, 128, 70), (1000, 200, 5)])
+@pytest.mark.parametrize("n,d,nq", [(3000, 768, 130), (2500, 128, 70), (1000, 200, 5), (1500, 1536, 140), (700, 800, 9)])
 def test_filter_scores_match_bf16_emulation(metric, n, d, nq):
     db, q = gaussian(n, d, 1), gaussian(nq, d, 2)
     s = DeviceStore(d, metric)
@@ -51,7 +51,8 @@ def test_filter_scores_match_bf16_emulation(metric, n, d, nq):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 300, 10), (6000, 128, 130, 10), (9999, 200, 77, 1), (5000, 64, 129, 24)])
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 300, 10), (6000, 128, 130, 10), (9999, 200, 77, 1), (5000, 64, 129, 24),
+                                      (9000, 1536, 260, 10), (5000, 1000, 33, 24)])
 def test_tensor_path_bit_exact_vs_oracle(metric, n, d, nq, k):
     db, q = gaussian(n, d, 1234), gaussian(nq, d, 4321)
     s = DeviceStore(d, metric)
@@ -123,7 +124,8 @@ def test_near_duplicates_cluster():
 
 def test_auto_dispatch():
     # large stores: the tensor filter serves every batch size (it streams the bf16 mirror, half the
-    # bytes of the fp32 scan); small stores and dims beyond the TMEM budget use the exact scan
+    # bytes of the fp32 scan), dims beyond the TMEM budget through the smem-streamed variant; small
+    # stores use the exact scan
     s = DeviceStore(128, DistanceMetric.L2)
     s.append(gaussian(8192, 128, 1))
     s.search_flat(gaussian(1, 128, 2), 10)
@@ -143,7 +145,7 @@ def test_auto_dispatch():
     db, q = gaussian(5000, 1536, 1), gaussian(20, 1536, 2)
     s.append(db)
     ids, dist, _ = s.search_flat(q, 10)
-    assert s.last_counters()[0] == 0
+    assert s.last_counters()[0] == 20
     o = oracle.flat_search(3, db, q, 10, nthreads=8)
     assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
     s.close()

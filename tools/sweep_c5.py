@@ -65,10 +65,6 @@ def main():
                                            C.c_void_p(out_dist.data_ptr()), C.c_void_p(out_cnt.data_ptr()), stream))
 
         for nq in batches:
-            # keep the slow exact path bounded: it is linear in nq/8 passes
-            exact_only = dim > 768
-            if exact_only and nq > 4096:
-                continue
             store.set_option("profile", 0)
             for _ in range(3):
                 run(nq)
