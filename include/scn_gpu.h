@@ -19,6 +19,8 @@
  *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
  *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
  *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev
+ *   Collection.Compact (drop deleted, rebuild)             scn_store_compact          (collection.go:283-313)
+ *   Collection.Search called by many goroutines            scn_batcher_search         (collection.go:193-204)
  *
  * Status codes are the reference's utils.ErrorCode numbers (internal/utils/errors.go:11-49) so the
  * Go shim can wrap them with utils.NewError(code, scn_last_error()).
@@ -108,6 +110,12 @@ SCN_API int32_t scn_store_append_dev(scn_store* s, const float* d_vecs, const ui
 /* Soft delete (HNSW.Delete). Unknown id -> SCN_ERR_VECTOR_NOT_FOUND; already deleted is a no-op. */
 SCN_API int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n);
 
+/* Collection.Compact (collection.go:283-313): physically removes the soft-deleted rows. Surviving
+ * rows keep their insertion order and ids; the graph is dropped (the reference rebuilds the index
+ * from the survivors and the host hands the new graph over with scn_graph_upload). out_removed
+ * (may be NULL) = rows dropped. */
+SCN_API int32_t scn_store_compact(scn_store* s, uint64_t* out_removed);
+
 SCN_API int32_t scn_store_stats(scn_store* s, scn_stats* out);
 
 /* Copies row vectors back to the host by id (HNSW.Get); out is [n][dim]. */
@@ -162,6 +170,23 @@ SCN_API int32_t scn_search_flat_shard_dev(scn_store* s, const float* d_q, uint64
  * the global top-k with the flat scan's (distance, row) order. */
 SCN_API int32_t scn_merge_topk_dev(int32_t device, const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq,
                            uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/* ---- micro-batching of single-query calls ------------------------------------
+ * The reference's API is one query per call (Collection.Search, collection.go:193-204; HNSW.Search,
+ * hnsw.go:292-350) issued by many goroutines at once. scn_batcher_search is the drop-in for that
+ * call: blocking, one query, callable from any number of threads; calls in flight at the same time
+ * are coalesced into one batched launch (leader/follower, no background thread). kind: 0 = exact
+ * flat scan, 1 = HNSW (ef as in scn_search_hnsw; ignored for kind 0). A batch is dispatched when it
+ * holds max_batch queries, or window_us after its first query arrived provided fewer than two
+ * batches are executing (under load batches grow to whatever arrived meanwhile). Results are those
+ * of scn_search_flat / scn_search_hnsw for the same query. */
+typedef struct scn_batcher scn_batcher;
+SCN_API int32_t scn_batcher_create(scn_store* s, int32_t kind, uint32_t max_batch, uint32_t window_us, scn_batcher** out);
+SCN_API int32_t scn_batcher_destroy(scn_batcher* b);
+SCN_API int32_t scn_batcher_search(scn_batcher* b, const float* q, uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
+                           uint32_t* out_count);
+/* out[0] calls, [1] batches, [2] batched launches, [3] largest batch so far. */
+SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
 
 /* ---- tuning / introspection ---------------------------------------------------------------- */
 /* Options: "flat_path" 0 = auto, 1 = exact CUDA-core scan only, 2 = tensor-core filter + exact

@@ -33,6 +33,7 @@ SIGNATURES = {
     "scn_store_append": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "scn_store_append_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "scn_store_mark_deleted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_store_compact": (C.c_int32, [C.c_void_p, u64p]),
     "scn_store_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
     "scn_store_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "scn_graph_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
@@ -52,6 +53,10 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p]),
     "scn_merge_topk_dev": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_batcher_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "scn_batcher_destroy": (C.c_int32, [C.c_void_p]),
+    "scn_batcher_search": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_batcher_stats": (C.c_int32, [C.c_void_p, u64p, C.c_int32]),
     "scn_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
     "scn_last_timings": (C.c_int32, [C.c_void_p, C.POINTER(C.c_char_p), f32p, u32p, C.c_int32]),
     "scn_last_counters": (C.c_int32, [C.c_void_p, u64p, C.c_int32]),

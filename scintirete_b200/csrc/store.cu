@@ -120,6 +120,41 @@ int32_t launch_prepare_rows(scn_store* s, uint64_t first_row, uint64_t n, cudaSt
   return SCN_OK;
 }
 
+// ---- compaction gather: dst[new_row] = src[src_row[new_row]], rows of `bytes` bytes (multiple of 4) --
+__global__ void __launch_bounds__(256) gather_rows_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst,
+                                                          const uint32_t* __restrict__ src_row, uint64_t n_new, uint32_t bytes) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n_new) return;
+  const unsigned char* s = src + (uint64_t)src_row[warp] * bytes;
+  unsigned char* d = dst + warp * bytes;
+  if ((bytes & 15u) == 0) {
+    for (uint32_t i = lane; i < bytes / 16; i += 32) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (uint32_t i = lane; i < bytes / 4; i += 32) reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+  }
+}
+
+template <class T>
+static int32_t gather_array(T** arr, const uint32_t* d_src_row, uint64_t n_new, uint64_t new_cap, uint32_t elems_per_row,
+                            cudaStream_t st) {
+  T* np = nullptr;
+  SCN_CUDA(cudaMalloc(&np, std::max<uint64_t>(new_cap * elems_per_row, 1) * sizeof(T)));
+  SCN_CUDA(cudaMemsetAsync(np, 0, std::max<uint64_t>(new_cap * elems_per_row, 1) * sizeof(T), st));
+  if (n_new) {
+    const uint32_t bytes = elems_per_row * (uint32_t)sizeof(T);
+    const uint64_t threads = n_new * 32;
+    gather_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(reinterpret_cast<const unsigned char*>(*arr),
+                                                                          reinterpret_cast<unsigned char*>(np), d_src_row, n_new,
+                                                                          bytes);
+    SCN_LAUNCHED();
+  }
+  SCN_CUDA(cudaStreamSynchronize(st));
+  cudaFree(*arr);
+  *arr = np;
+  return SCN_OK;
+}
+
 }  // namespace scn
 
 using namespace scn;
@@ -365,6 +400,56 @@ int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
   SCN_CUDA(cudaStreamSynchronize(st));
   // the tensor filter learns about deletions through its per-row additive term (+Inf)
   return mark_aux_deleted(s, rows.data(), (uint32_t)rows.size(), st);
+}
+
+// Collection.Compact (collection.go:283-313): drop the soft-deleted vectors for good. Surviving
+// rows keep their insertion order (and their ids); the graph is dropped, because the reference
+// rebuilds the index from the surviving vectors (index.Build) and hands the new graph over again.
+int32_t scn_store_compact(scn_store* s, uint64_t* out_removed) {
+  if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
+  DeviceGuard g(s->device);
+  cudaDeviceSynchronize();
+  if (out_removed) *out_removed = s->rows - s->live;
+  free_graph(s);
+  if (s->live == s->rows) return SCN_OK;
+  cudaStream_t st = thread_stream(s->device);
+  const size_t words = (s->rows + 31) / 32;
+  std::vector<uint32_t> bits(words);
+  SCN_CUDA(cudaMemcpy(bits.data(), s->d_deleted, words * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> src_row;
+  src_row.reserve(s->live);
+  for (uint64_t r = 0; r < s->rows; ++r)
+    if (!((bits[r >> 5] >> (r & 31)) & 1u)) src_row.push_back((uint32_t)r);
+  const uint64_t n_new = src_row.size();
+  // ids of the survivors: the implicit id = row + 1 rule no longer holds once a row is gone
+  std::vector<uint64_t> old_ids;
+  if (!s->auto_ids) {
+    old_ids.resize(s->rows);
+    SCN_CUDA(cudaMemcpy(old_ids.data(), s->d_ids, s->rows * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  std::unordered_map<uint64_t, uint32_t> row_of;
+  row_of.reserve(n_new * 2);
+  for (uint64_t i = 0; i < n_new; ++i) row_of[s->auto_ids ? (uint64_t)src_row[i] + 1 : old_ids[src_row[i]]] = (uint32_t)i;
+  uint32_t* d_src = nullptr;
+  SCN_CUDA(cudaMalloc(&d_src, std::max<uint64_t>(n_new, 1) * sizeof(uint32_t)));
+  SCN_CUDA(cudaMemcpy(d_src, src_row.data(), n_new * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  const uint64_t new_cap = std::max<uint64_t>((n_new + 255) / 256 * 256, 256);
+  int32_t rc = gather_array(&s->d_vec, d_src, n_new, new_cap, s->pitch, st);
+  if (rc == SCN_OK) rc = gather_array(&s->d_norm, d_src, n_new, new_cap, 1, st);
+  if (rc == SCN_OK) rc = gather_array(&s->d_mirror, d_src, n_new, new_cap, s->kpad, st);
+  if (rc == SCN_OK) rc = gather_array(&s->d_aux, d_src, n_new, new_cap, 1, st);
+  if (rc == SCN_OK) rc = gather_array(&s->d_ids, d_src, n_new, new_cap, 1, st);
+  cudaFree(d_src);
+  SCN_TRY(rc);
+  cudaFree(s->d_deleted);
+  s->d_deleted = nullptr;
+  SCN_CUDA(cudaMalloc(&s->d_deleted, ((new_cap + 31) / 32) * 4));
+  SCN_CUDA(cudaMemset(s->d_deleted, 0, ((new_cap + 31) / 32) * 4));
+  s->cap = new_cap;
+  s->rows = s->live = n_new;
+  s->auto_ids = false;
+  s->row_of.swap(row_of);
+  return SCN_OK;
 }
 
 int32_t scn_store_stats(scn_store* s, scn_stats* out) {

@@ -131,6 +131,13 @@ class DeviceStore:
         a = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
         _check(_native.lib().scn_store_mark_deleted(self._h, _ptr(a), a.size))
 
+    def compact(self) -> int:
+        """Collection.Compact (collection.go:283-313), device half: drops the soft-deleted rows and the
+        graph; returns the number of rows removed."""
+        n = C.c_uint64(0)
+        _check(_native.lib().scn_store_compact(self._h, C.byref(n)))
+        return int(n.value)
+
     def stats(self) -> _native.Stats:
         st = _native.Stats()
         _check(_native.lib().scn_store_stats(self._h, C.byref(st)))
@@ -197,6 +204,39 @@ class DeviceStore:
         return ids, dist, cnt
 
 
+class Batcher:
+    """scn_batcher: coalesces concurrent single-query searches (the reference's one-query-per-call
+    API, collection.go:193-204, called from many goroutines) into batched launches."""
+
+    FLAT, HNSW = 0, 1
+
+    def __init__(self, store: DeviceStore, kind: int, max_batch: int = 1024, window_us: int = 100):
+        h = C.c_void_p()
+        _check(_native.lib().scn_batcher_create(store.handle, kind, max_batch, window_us, C.byref(h)))
+        self._h, self._store, self.kind = h, store, kind
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _check(_native.lib().scn_batcher_destroy(h))
+
+    def search(self, query, k: int, ef: int = 0) -> Tuple[np.ndarray, np.ndarray, int]:
+        """One query, blocking; safe to call from many threads at once (ctypes drops the GIL)."""
+        q = _f32(query).ravel()
+        if q.size != self._store.dim:
+            raise ScintireteError(ErrorCode.DIMENSION_MISMATCH, f"query has dimension {q.size}, expected {self._store.dim}")
+        ids = np.zeros(max(k, 1), np.uint64)
+        dist = np.full(max(k, 1), np.inf, np.float32)
+        cnt = C.c_uint32(0)
+        _check(_native.lib().scn_batcher_search(self._h, _ptr(q), k, ef, _ptr(ids), _ptr(dist), C.byref(cnt)))
+        return ids, dist, int(cnt.value)
+
+    def stats(self) -> Dict[str, int]:
+        c = (C.c_uint64 * 4)()
+        _check(_native.lib().scn_batcher_stats(self._h, c, 4))
+        return {"calls": int(c[0]), "batches": int(c[1]), "launches": int(c[2]), "max_batch": int(c[3])}
+
+
 # ---- VectorIndex / HNSWIndex ---------------------------------------------------------------------
 
 class _GPUIndexBase:
@@ -214,6 +254,17 @@ class _GPUIndexBase:
         self.store = DeviceStore(dim, m, device)
         self._metadata: Dict[int, Dict[str, Any]] = {}
         self._deleted: set = set()
+        self._batcher: Optional[Batcher] = None
+
+    def enable_micro_batching(self, max_batch: int = 1024, window_us: int = 100) -> None:
+        """Route single-query search() calls through a Batcher so that concurrent callers share
+        one batched launch."""
+        kind = Batcher.HNSW if isinstance(self, GPUHNSWIndex) else Batcher.FLAT
+        self._batcher = Batcher(self.store, kind, max_batch, window_us)
+
+    def _search_one(self, query, k: int, ef: int):
+        ids, dist, n = self._batcher.search(query, k, ef)
+        return ids[None, :], dist[None, :], np.array([n], np.uint32)
 
     # -- mutation --
     def insert(self, vector: Vector) -> None:
@@ -284,7 +335,17 @@ class GPUFlatIndex(_GPUIndexBase):
         return self.store.search_flat(queries, params.top_k)
 
     def search(self, query, params: SearchParams, include_vector: bool = False) -> List[SearchResult]:
+        if self._batcher is not None and params.top_k > 0:
+            return self._results(*self._search_one(query, params.top_k, 0), include_vector)[0]
         return self._results(*self.search_batch(_f32(query)[None, :], params), include_vector)[0]
+
+    def compact(self) -> int:
+        """Collection.Compact for the flat index: the deleted rows are dropped on the device."""
+        n = self.store.compact()
+        for vid in self._deleted:
+            self._metadata.pop(vid, None)
+        self._deleted.clear()
+        return n
 
     def get_statistics(self):
         st = self.store.stats()
@@ -351,6 +412,8 @@ class GPUHNSWIndex(_GPUIndexBase):
         return self.store.search_hnsw(queries, params.top_k, self._ef(params))
 
     def search(self, query, params: SearchParams, include_vector: bool = False) -> List[SearchResult]:
+        if self._batcher is not None and params.top_k > 0:
+            return self._results(*self._search_one(query, params.top_k, self._ef(params)), include_vector)[0]
         return self._results(*self.search_batch(_f32(query)[None, :], params), include_vector)[0]
 
     def search_exact(self, queries, params: SearchParams):
