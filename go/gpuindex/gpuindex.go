@@ -52,6 +52,22 @@ type GPUIndex struct {
 	params types.HNSWParams
 	dirty  bool // CPU graph changed since the last upload
 	flat   bool // "flat-gpu": Search is the exact scan, no graph needed
+
+	// batcher coalesces the one-query Search calls of concurrent goroutines (collection.go:193-204
+	// is called once per request) into batched launches; nil = every Search is its own launch.
+	batcher *C.scn_batcher
+}
+
+// EnableMicroBatching routes Search through scn_batcher_search: a batch is dispatched when it holds
+// maxBatch queries or windowMicros after its first query arrived.
+func (g *GPUIndex) EnableMicroBatching(maxBatch, windowMicros int) error {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	kind := C.int32_t(1)
+	if g.flat {
+		kind = 0
+	}
+	return scnErr(C.scn_batcher_create(g.store, kind, C.uint32_t(maxBatch), C.uint32_t(windowMicros), &g.batcher))
 }
 
 func scnErr(rc C.int32_t) error {
@@ -80,6 +96,10 @@ func New(params types.HNSWParams, metric types.DistanceMetric, dim int, device i
 func (g *GPUIndex) Close() {
 	g.mu.Lock()
 	defer g.mu.Unlock()
+	if g.batcher != nil {
+		C.scn_batcher_destroy(g.batcher)
+		g.batcher = nil
+	}
 	if g.store != nil {
 		C.scn_store_destroy(g.store)
 		g.store = nil
@@ -284,11 +304,62 @@ func (g *GPUIndex) Search(ctx context.Context, query []float32, p types.SearchPa
 	if len(query) != g.dim {
 		return nil, utils.ErrInvalidVectorDimension(fmt.Sprintf("query has dimension %d, expected %d", len(query), g.dim))
 	}
+	if g.batcher != nil && p.TopK > 0 {
+		return g.searchCoalesced(ctx, query, p)
+	}
 	r, err := g.SearchBatch(ctx, query, p)
 	if err != nil {
 		return nil, err
 	}
 	return r[0], nil
+}
+
+// searchCoalesced is Search through the micro-batcher: this goroutine blocks in cgo until the
+// batch its query joined has been answered.
+func (g *GPUIndex) searchCoalesced(ctx context.Context, query []float32, p types.SearchParams) ([]types.SearchResult, error) {
+	g.mu.RLock()
+	if g.dirty {
+		g.mu.RUnlock()
+		g.mu.Lock()
+		err := g.syncGraph()
+		g.mu.Unlock()
+		if err != nil {
+			return nil, err
+		}
+		g.mu.RLock()
+	}
+	defer g.mu.RUnlock()
+	k := p.TopK
+	ids := make([]C.uint64_t, k)
+	dist := make([]C.float, k)
+	var cnt C.uint32_t
+	rc := C.scn_batcher_search(g.batcher, (*C.float)(unsafe.Pointer(&query[0])), C.uint32_t(k), C.uint32_t(g.ef(p)),
+		&ids[0], &dist[0], &cnt)
+	if rc != 0 {
+		return nil, scnErr(rc)
+	}
+	res := make([]types.SearchResult, 0, int(cnt))
+	for j := 0; j < int(cnt); j++ {
+		id := uint64(ids[j])
+		r := types.SearchResult{Vector: types.Vector{ID: id}, Distance: float32(dist[j])}
+		if v, err := g.HNSWIndex.Get(ctx, fmt.Sprintf("%d", id)); err == nil && v != nil {
+			r.Vector = *v
+		}
+		res = append(res, r)
+	}
+	return res, nil
+}
+
+// Compact is the device half of Collection.Compact (collection.go:283-313): the caller rebuilds the
+// CPU index from the surviving vectors (index.Build); here the deleted rows leave HBM and the stale
+// graph is dropped, to be uploaded again before the next search.
+func (g *GPUIndex) Compact() (int, error) {
+	g.mu.Lock()
+	defer g.mu.Unlock()
+	var removed C.uint64_t
+	rc := C.scn_store_compact(g.store, &removed)
+	g.dirty = true
+	return int(removed), scnErr(rc)
 }
 
 // SearchExact is the flat ground truth over the same rows.

@@ -28,6 +28,21 @@ void count_launch(uint64_t n = 1);
     if (rc__ != SCN_OK) return rc__; \
   } while (0)
 
+// Opt-in dynamic shared memory. Search entry points run concurrently from many host threads, so the
+// per-function limit must never be lowered between another thread's set and its launch: every call
+// sets the SAME value, the device's opt-in maximum (idempotent, hence race-free).
+int max_optin_smem();
+int static_smem_of(const void* kernel);
+#define SCN_ALLOW_SMEM(kernel, bytes)                                                                     \
+  do {                                                                                                    \
+    static const int static__ = scn::static_smem_of((const void*)(kernel)); /* statically allocated part */ \
+    const int limit__ = scn::max_optin_smem() - static__;                                                 \
+    if ((size_t)(bytes) > (size_t)limit__)                                                                \
+      return scn::fail(SCN_ERR_INVALID_PARAMETERS, "%zu bytes of shared memory exceed the device limit",   \
+                       (size_t)(bytes));                                                                  \
+    SCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit__));         \
+  } while (0)
+
 // after a kernel launch
 #define SCN_LAUNCHED()                                                         \
   do {                                                                         \

@@ -249,7 +249,7 @@ static size_t scan_smem_bytes(int qb, uint32_t dim_pad, uint32_t k) {
 
 template <int METRIC, int QB>
 static int32_t launch_scan(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
-  SCN_CUDA(cudaFuncSetAttribute(flat_exact_scan_kernel<METRIC, QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SCN_ALLOW_SMEM((flat_exact_scan_kernel<METRIC, QB>), smem);
   flat_exact_scan_kernel<METRIC, QB><<<grid, SCAN_THREADS, smem, stream>>>(p);
   SCN_LAUNCHED();
   return SCN_OK;
@@ -417,7 +417,7 @@ int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t*
   const unsigned grid = d_qlist ? (unsigned)std::min<uint64_t>(nq, 592) : (unsigned)nq;
 #define RR(MT)                                                                                                    \
   do {                                                                                                            \
-    SCN_CUDA(cudaFuncSetAttribute(rerank_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    SCN_ALLOW_SMEM((rerank_kernel<MT>), smem);    \
     rerank_kernel<MT><<<grid, threads, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,      \
                                                        (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k,  \
                                                        (uint32_t)row_base, d_qlist, d_nq_dev, (uint32_t)nq, d_out_keys); \

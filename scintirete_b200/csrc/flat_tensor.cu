@@ -633,7 +633,7 @@ static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
                 (size_t)2 * TF_BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
-  SCN_CUDA(cudaFuncSetAttribute(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM>), smem);
   tensor_filter_kernel<KP, NBUF, EW, DBG, ASM><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
   SCN_LAUNCHED();
   return SCN_OK;
@@ -751,7 +751,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(rc);
 
   if ((size_t)n_pad * 8 > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many candidate lists (%u) for one merge block", n_lists);
-  SCN_CUDA(cudaFuncSetAttribute(merge_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)n_pad * 8)));
+  SCN_ALLOW_SMEM((merge_candidates_kernel), ((size_t)n_pad * 8));
   if (prof) prof->begin("merge_candidates");
   merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime, n_pad, kpp,
                                                                             d_rows, d_tau, d_tau_chunks);

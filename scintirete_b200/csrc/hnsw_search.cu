@@ -422,7 +422,7 @@ template <int METRIC>
 static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
   // pass 1: shared-memory visited table
   const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false) * HNSW_WARPS;
-  SCN_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<METRIC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, false>), smem);
   int per_sm = 0;
   SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false>, HNSW_WARPS * 32, smem));
   if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
@@ -446,7 +446,7 @@ static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& s
   const int grid2 = std::min<int>(sms, (int)blocks_needed);
   SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * HNSW_WARPS * b.hash_size));
   const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true) * HNSW_WARPS;
-  SCN_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<METRIC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true>), smem2);
   if (prof) prof->begin("hnsw_search_overflow");
   hnsw_search_kernel<METRIC, true><<<grid2, HNSW_WARPS * 32, smem2, stream>>>(b);
   SCN_LAUNCHED();

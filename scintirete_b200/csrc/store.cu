@@ -28,6 +28,26 @@ int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int max_optin_smem() {
+  // all devices of a box are the same part (the library refuses anything but sm_100)
+  static const int v = [] {
+    int dev = 0, val = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&val, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return val;
+  }();
+  return v;
+}
+
+int static_smem_of(const void* kernel) {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) {
+    cudaGetLastError();
+    return 1024;
+  }
+  return (int)fa.sharedSizeBytes;
+}
+
 cudaStream_t thread_stream(int device) {
   // one non-blocking stream per (host thread, device): concurrent Search calls from different
   // goroutines/threads overlap on the GPU (the reference allows concurrent readers, hnsw.go:293)

@@ -148,3 +148,28 @@ def test_flat_index_compact_mirrors_collection_compact():
     assert idx.compact() == 2 and idx.size() == 8
     res = idx.search([2.2, 0, 0, 0], SearchParams(top_k=3))
     assert [r.vector.id for r in res] == [2, 5, 1]
+
+
+def test_concurrent_uncoalesced_searches_with_different_shapes():
+    # The reference allows any number of concurrent Search calls under RLock (hnsw.go:293). Calls of
+    # different shapes need different amounts of dynamic shared memory; the per-kernel opt-in limit
+    # must not be lowered by one thread between another thread's set and its launch.
+    n, d = 12000, 64
+    db = gaussian(n, d, 1)
+    s = DeviceStore(d, DistanceMetric.L2)
+    s.append(db)
+    shapes = [(1, 1), (3, 10), (40, 24), (7, 100), (130, 5), (2, 300)]
+    want = {}
+    for nq, k in shapes:
+        q = gaussian(nq, d, 100 + nq)
+        want[(nq, k)] = (q, oracle.flat_search(1, db, q, k, nthreads=4))
+
+    def work(t):
+        for rep in range(12):
+            nq, k = shapes[(t + rep) % len(shapes)]
+            q, o = want[(nq, k)]
+            ids, dist, _ = s.search_flat(q, k)
+            assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+
+    _run_threads(24, work)
+    s.close()
