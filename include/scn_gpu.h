@@ -19,6 +19,7 @@
  *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
  *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
  *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev
+ *   RDBManager.Load + RestoreFromSnapshot + ImportGraph    scn_store_load_rdb         (rdb.go:179-237, database.go:398-493)
  *   Collection.Compact (drop deleted, rebuild)             scn_store_compact          (collection.go:283-313)
  *   Collection.Search called by many goroutines            scn_batcher_search         (collection.go:193-204)
  *
@@ -131,6 +132,31 @@ SCN_API int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, flo
 SCN_API int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t entry_id, uint64_t n_nodes,
                          const uint64_t* node_ids, const int32_t* list_counts, const uint32_t* edge_counts,
                          const uint64_t* edges);
+
+/* ---- restore from an RDB snapshot ---------------------------------------------
+ * Reads one collection of a snapshot written by the reference (schemas/flatbuffers/rdb.fbs,
+ * rdb.go:239-533) straight into a new device store: vectors, ids, soft-delete flags and the HNSW
+ * graph, with the semantics of RDBManager.Load -> ConvertHNSWGraphSnapshot -> ImportGraphState
+ * (rdb.go:179-237, 1027-1091; database.go:398-493; hnsw.go:749-804): lists above a node's max_layer
+ * are dropped, unparsable neighbour ids are skipped, a snapshot without graph state is refused.
+ * Errors: 4001 (recovery failed), 4002 (corrupted data), 3000 / 3002 (database / collection not in
+ * the file), 3005 (nodes of different dimension). info (may be NULL) receives the collection's
+ * configuration and counts, also when the load itself fails after parsing. */
+typedef struct scn_rdb_info {
+  int32_t metric;          /* CollectionConfig.metric */
+  uint32_t dim;            /* length of the nodes' element arrays */
+  int32_t m, ef_construction, ef_search, max_layers;   /* HNSWParams */
+  int64_t seed;
+  uint64_t nodes;          /* nodes in the graph (including soft-deleted) */
+  uint64_t deleted;        /* of those, soft-deleted */
+  uint64_t entry_id;       /* HNSWGraph.entrypoint_id */
+  int32_t max_layer;       /* HNSWGraph.max_layer */
+  int32_t graph_size;      /* HNSWGraph.size */
+  int64_t vector_count, deleted_count;   /* CollectionSnapshot counters */
+  int32_t has_graph;
+} scn_rdb_info;
+SCN_API int32_t scn_store_load_rdb(const char* path, const char* database, const char* collection, int32_t device,
+                           scn_store** out, scn_rdb_info* info);
 
 /* ---- search (host buffers; blocking) -------------------------------------------------------
  * q is [nq][dim] fp32. Outputs are [nq][k]: ids (0 = none) and distances (+Inf = none), sorted by

@@ -22,6 +22,13 @@ class Stats(C.Structure):
                 ("graph_edges", C.c_uint64)]
 
 
+class RdbInfo(C.Structure):
+    _fields_ = [("metric", C.c_int32), ("dim", C.c_uint32), ("m", C.c_int32), ("ef_construction", C.c_int32),
+                ("ef_search", C.c_int32), ("max_layers", C.c_int32), ("seed", C.c_int64), ("nodes", C.c_uint64),
+                ("deleted", C.c_uint64), ("entry_id", C.c_uint64), ("max_layer", C.c_int32), ("graph_size", C.c_int32),
+                ("vector_count", C.c_int64), ("deleted_count", C.c_int64), ("has_graph", C.c_int32)]
+
+
 # every symbol include/scn_gpu.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "scn_last_error": (C.c_char_p, []),
@@ -53,6 +60,8 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p]),
     "scn_merge_topk_dev": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_store_load_rdb": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p),
+                                        C.POINTER(RdbInfo)]),
     "scn_batcher_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "scn_batcher_destroy": (C.c_int32, [C.c_void_p]),
     "scn_batcher_search": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -97,6 +97,19 @@ class DeviceStore:
         self._h = h
         self.dim, self.metric, self.device = dim, DistanceMetric(metric), device
 
+    @classmethod
+    def from_rdb(cls, path: str, database: str, collection: str, device: int = 0) -> Tuple["DeviceStore", "_native.RdbInfo"]:
+        """Restore one collection of a reference-written RDB snapshot straight into device memory
+        (RDBManager.Load -> RestoreFromSnapshot -> ImportGraphState; rdb.go:179-237, database.go:398-493)."""
+        h = C.c_void_p()
+        info = _native.RdbInfo()
+        _check(_native.lib().scn_store_load_rdb(str(path).encode(), database.encode(), collection.encode(), device,
+                                                C.byref(h), C.byref(info)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.dim, self.metric, self.device = int(info.dim), DistanceMetric(info.metric), device
+        return self, info
+
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
