@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
 }
 
 // ---- candidate merge: chunk lists -> k'' rows + tau -------------------------------------------------
-__global__ void __launch_bounds__(128) merge_candidates_kernel(const float* __restrict__ cand_score,
+__global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __restrict__ cand_score,
                                                                const uint32_t* __restrict__ cand_row,
                                                                const float* __restrict__ chunk_tau, uint32_t n_chunks,
                                                                uint32_t kprime, uint32_t n_pad, uint32_t kpp,
@@ -753,7 +753,8 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   if ((size_t)n_pad * 8 > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many candidate lists (%u) for one merge block", n_lists);
   SCN_ALLOW_SMEM((merge_candidates_kernel), ((size_t)n_pad * 8));
   if (prof) prof->begin("merge_candidates");
-  merge_candidates_kernel<<<(unsigned)nq, 128, (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime, n_pad, kpp,
+  // one block per query; long candidate lists (small batches: many chunks) get more threads per sort
+  merge_candidates_kernel<<<(unsigned)nq, std::min(512u, std::max(128u, n_pad / 4)), (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime, n_pad, kpp,
                                                                             d_rows, d_tau, d_tau_chunks);
   SCN_LAUNCHED();
   if (prof) prof->end();
