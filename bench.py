@@ -286,6 +286,34 @@ def run_ours(args, wl):
     h_dist = torch.zeros((nq, k), dtype=torch.float32).pin_memory()
     h_cnt = torch.zeros((nq,), dtype=torch.int32).pin_memory()
 
+    # Row-sharded exchange: fused into the search epilogue over NVLink peer memory (P2P stores +
+    # flags, scn_search_flat_exchange_dev), or the NCCL formulation (2 all-gathers + merge).
+    merge_mode, exchange = "none", None
+    if world > 1 and kind == "flat":
+        merge_mode = args.merge
+        if merge_mode == "p2p":
+            from scintirete_b200.sharding import ShardExchange
+
+            handle = None
+            try:
+                exchange = ShardExchange(local, rank, world, nq, k)
+                handle = exchange.local_handle()
+            except Exception as e:
+                print(f"[rank {rank}] peer-memory exchange unavailable ({e})", file=sys.stderr)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)          # every rank takes part, whatever happened above
+            ok = torch.ones(1, device=dev)
+            try:
+                if any(h is None for h in handles):
+                    raise RuntimeError("a rank could not create its exchange buffer")
+                exchange.connect(handles)
+            except Exception as e:  # e.g. CUDA IPC not permitted in this container
+                print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks must agree on the protocol
+            if ok.item() == 0:
+                exchange, merge_mode = None, "nccl"
+
     def p(t):
         return C.c_void_p(t.data_ptr())
 
@@ -295,6 +323,9 @@ def run_ours(args, wl):
             _check(lib.scn_search_hnsw_dev(store.handle, p(qd), nq, k, args.ef, p(out_ids), p(out_dist), p(out_cnt), stream))
         elif world == 1 and kind == "flat":
             _check(lib.scn_search_flat_dev(store.handle, p(qd), nq, k, p(out_ids), p(out_dist), p(out_cnt), stream))
+        elif exchange is not None:
+            exchange.search(store, qd.data_ptr(), nq, row0, out_ids.data_ptr(), out_dist.data_ptr(), out_cnt.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
         else:
             _check(lib.scn_search_flat_shard_dev(store.handle, p(qd), nq, k, row0, p(keys), p(out_ids), stream))
             dist.all_gather_into_tensor(all_keys, keys)
@@ -425,6 +456,8 @@ def run_ours(args, wl):
                                    + (f" ef={args.ef}" if kind == "hnsw" else ""),
                        "rows": rows, "dim": dim, "metric": METRIC_NAME[metric], "nq": nq, "k": k,
                        "sharding": f"rows/{world}" if kind == "flat" else f"replicas x{world}, query batch split",
+                       "shard_merge": {"p2p": "fused into the search epilogue over NVLink peer memory (P2P stores + flags)",
+                                       "nccl": "NCCL all_gather of keys and ids + merge kernel", "none": None}[merge_mode],
                        "l2_policy": "database (>= 3 GB fp32 + bf16 mirror per pass) is far larger than the 126 MB L2; no flush needed"
                        if rows * dim * 4 > 4e8 else "working set fits L2: flush not applied (small workload, not the headline)"},
             "e2e": {"value": nq_job * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
@@ -434,6 +467,10 @@ def run_ours(args, wl):
             "counters": counters,
         }
         print(json.dumps(line), flush=True)
+    if exchange is not None:
+        exchange.status(torch.cuda.current_stream().cuda_stream)   # a missed peer arrival would have invalidated the run
+        barrier()
+        exchange.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,6 +487,7 @@ def main():
     ap.add_argument("--nq", type=int)
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="row-shard exchange for --gpus > 1")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.rows:

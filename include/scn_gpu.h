@@ -18,7 +18,7 @@
  *   HNSW.Search rerank step on caller-chosen candidates    scn_rerank                 (hnsw.go:317-347)
  *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
  *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
- *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev
+ *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev, scn_search_flat_exchange_dev
  *   RDBManager.Load + RestoreFromSnapshot + ImportGraph    scn_store_load_rdb         (rdb.go:179-237, database.go:398-493)
  *   Collection.Compact (drop deleted, rebuild)             scn_store_compact          (collection.go:283-313)
  *   Collection.Search called by many goroutines            scn_batcher_search         (collection.go:193-204)
@@ -196,6 +196,27 @@ SCN_API int32_t scn_search_flat_shard_dev(scn_store* s, const float* d_q, uint64
  * the global top-k with the flat scan's (distance, row) order. */
 SCN_API int32_t scn_merge_topk_dev(int32_t device, const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq,
                            uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/* ---- row-sharded search with the shard exchange fused over NVLink peer memory -------------------
+ * One scn_exchange per rank (= per GPU / row shard). The epilogue of the shard-local search stores
+ * its top-k (key, id) lists straight into every rank's exchange buffer (P2P stores) and raises a
+ * flag there; each rank then merges from its own memory. Replaces the all_gather + merge of the
+ * NCCL formulation; results are bit-identical to the single-GPU search. Every rank must call
+ * scn_search_flat_exchange_dev for the same batch (same nq), like a collective.
+ *   between processes : exchange the 64-byte handles (any transport), then scn_exchange_connect
+ *   inside one process: scn_exchange_connect_local with the peers' objects */
+#define SCN_IPC_HANDLE_BYTES 64
+typedef struct scn_exchange scn_exchange;
+SCN_API int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint64_t max_nq, uint32_t k, scn_exchange** out);
+SCN_API int32_t scn_exchange_local_handle(scn_exchange* ex, void* out_handle);
+SCN_API int32_t scn_exchange_connect(scn_exchange* ex, const void* handles /* [world][64] */);
+SCN_API int32_t scn_exchange_connect_local(scn_exchange* ex, scn_exchange* const* peers /* [world] */);
+SCN_API int32_t scn_exchange_destroy(scn_exchange* ex);
+SCN_API int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, uint64_t nq, uint32_t k,
+                                     uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                                     void* stream);
+/* Synchronises `stream`; SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out. */
+SCN_API int32_t scn_exchange_status(scn_exchange* ex, void* stream);
 
 /* ---- micro-batching of single-query calls ------------------------------------
  * The reference's API is one query per call (Collection.Search, collection.go:193-204; HNSW.Search,

@@ -62,6 +62,14 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scn_store_load_rdb": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p),
                                         C.POINTER(RdbInfo)]),
+    "scn_exchange_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "scn_exchange_local_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "scn_exchange_connect": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "scn_exchange_connect_local": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "scn_exchange_destroy": (C.c_int32, [C.c_void_p]),
+    "scn_search_flat_exchange_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_exchange_status": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "scn_batcher_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "scn_batcher_destroy": (C.c_int32, [C.c_void_p]),
     "scn_batcher_search": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

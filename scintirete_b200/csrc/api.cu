@@ -18,7 +18,7 @@ static int32_t check_search_args(scn_store* s, const void* q, uint64_t nq, uint3
 }
 
 // shard-local flat search producing sorted keys [nq][k]
-static int32_t flat_keys(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_keys,
+int32_t scn::flat_keys(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_keys,
                          cudaStream_t stream, Profiler* prof) {
   if (row_base + s->rows >= (uint64_t)ROW_NONE)
     return fail(SCN_ERR_INVALID_PARAMETERS, "global row index exceeds 32 bits");

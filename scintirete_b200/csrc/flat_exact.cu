@@ -473,7 +473,7 @@ int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const floa
 // One warp per query. Keys carry the global row, so ascending key order is exactly the flat
 // oracle's (distance, row) order over the whole database. ids ride along.
 __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ids,
-                                                         uint32_t n_shards, uint64_t nq, uint32_t k,
+                                                         uint32_t n_shards, uint64_t nq, uint32_t k, uint64_t shard_stride,
                                                          uint64_t* __restrict__ out_ids, float* __restrict__ out_dist,
                                                          uint32_t* __restrict__ out_counts) {
   uint64_t q = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     for (int i = 0; i < 8; ++i) {
       uint32_t sh = lane + 32 * i;
       if (sh < n_shards && head[i] < k) {
-        uint64_t v = keys[((size_t)sh * nq + q) * k + head[i]];
+        uint64_t v = keys[(size_t)sh * shard_stride + q * k + head[i]];
         if (v < best) {
           best = v;
           best_src = sh;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
     // the lane holding the winner (keys are unique: global rows differ) emits and advances
     if (best == wbest) {
       uint32_t i = best_src / 32;
-      out_ids[q * k + j] = ids[((size_t)best_src * nq + q) * k + head[i]];
+      out_ids[q * k + j] = ids[(size_t)best_src * shard_stride + q * k + head[i]];
       out_dist[q * k + j] = ord_f32((uint32_t)(wbest >> 32));
 #pragma unroll
       for (int t = 0; t < 8; ++t)
@@ -525,11 +525,11 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
 }
 
 int32_t merge_topk(const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq, uint32_t k,
-                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream) {
+                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, uint64_t shard_stride) {
   if (nq == 0) return SCN_OK;
   if (n_shards == 0 || n_shards > 256) return fail(SCN_ERR_INVALID_PARAMETERS, "n_shards must be in [1, 256]");
-  merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(d_keys, d_ids, n_shards, nq, k, d_out_ids, d_out_dist,
-                                                                  d_out_counts);
+  merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(d_keys, d_ids, n_shards, nq, k, shard_stride ? shard_stride : nq * k,
+                                                                  d_out_ids, d_out_dist, d_out_counts);
   SCN_LAUNCHED();
   return SCN_OK;
 }

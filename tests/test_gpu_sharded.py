@@ -55,3 +55,51 @@ def test_sharded_equals_single(metric, world, n, d, nq, k, path):
     assert np.array_equal(out_cnt.cpu().numpy().view(np.uint32), o_cnt)
     for s in stores:
         s.close()
+
+
+@pytest.mark.parametrize("metric", [DistanceMetric.L2, DistanceMetric.COSINE])
+@pytest.mark.parametrize("world,n,d,nq,k,path", [(2, 6001, 64, 40, 10, 1), (4, 30000, 128, 300, 10, 2), (8, 9000, 96, 130, 10, 0)])
+def test_fused_peer_exchange_equals_single(metric, world, n, d, nq, k, path):
+    # the shard exchange fused into the search epilogue (P2P stores + flags instead of all-gathers):
+    # G ranks of ONE process, each on its own stream, as the reference's single server process would
+    # drive its GPUs. Two rounds exercise the parity double buffering.
+    from scintirete_b200.sharding import ShardExchange
+
+    db = gaussian(n, d, 1234)
+    db[n // 2] = db[1]
+    ids_ext = np.arange(n, dtype=np.uint64) * 3 + 5
+    dev = torch.device("cuda", 0)
+    stores, exs, streams, outs = [], [], [], []
+    for r in range(world):
+        lo, hi = shard_range(n, world, r)
+        s = DeviceStore(d, metric)
+        s.set_option("flat_path", path)
+        s.append(db[lo:hi], ids_ext[lo:hi])
+        stores.append(s)
+        exs.append(ShardExchange(0, r, world, 512, k))
+        streams.append(torch.cuda.Stream(device=dev))
+        outs.append((torch.zeros((nq, k), dtype=torch.int64, device=dev), torch.zeros((nq, k), dtype=torch.float32, device=dev),
+                     torch.zeros((nq,), dtype=torch.int32, device=dev)))
+    for e in exs:
+        e.connect_local(exs)
+    for rnd in range(3):
+        q = gaussian(nq, d, 4321 + rnd)
+        q[0] = db[1]
+        qd = torch.from_numpy(q).to(dev)
+        torch.cuda.synchronize()
+        for r in range(world):
+            lo, _ = shard_range(n, world, r)
+            oi, od, oc = outs[r]
+            exs[r].search(stores[r], qd.data_ptr(), nq, lo, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), streams[r].cuda_stream)
+        for r in range(world):
+            exs[r].status(streams[r].cuda_stream)
+        o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, ids=ids_ext, nthreads=8)
+        for r in range(world):   # every rank ends up with the full, identical answer
+            oi, od, oc = outs[r]
+            assert np.array_equal(oi.cpu().numpy().view(np.uint64), o_ids)
+            assert np.array_equal(od.cpu().numpy(), o_dist)
+            assert np.array_equal(oc.cpu().numpy().view(np.uint32), o_cnt)
+    for e in exs:
+        e.close()
+    for s in stores:
+        s.close()
