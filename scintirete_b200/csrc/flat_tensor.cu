@@ -651,6 +651,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   const uint32_t n_qb = (uint32_t)((nq + TF_BM - 1) / TF_BM);
   const uint32_t nq_pad = n_qb * TF_BM;
   uint32_t n_chunks = pick_chunks(n_qb, n_tiles, (uint32_t)sms);
+  if (s->opt_tensor_chunks > 0) n_chunks = (uint32_t)std::min<int64_t>(s->opt_tensor_chunks, n_tiles);
   uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
   // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
