@@ -133,28 +133,37 @@ struct FilterArgs {
   float* dbg_scores;        // optional [nq][n_rows]
 };
 
-constexpr int TF_BN = 128;                        // database rows per tile (UMMA N)
 
 // KP   : candidates kept per (query, chunk, column slice); scores live in registers, rows in smem
 // NBUF : accumulator buffers in TMEM (2 when the A operand leaves room, else 1)
-// EW   : epilogue warps per TMEM lane quarter; each owns a slice of 128/EW columns of every tile.
+// EW   : epilogue warps per TMEM lane quarter; each owns a slice of BN/EW columns of every tile.
 //        Short K (small dim) makes the MMA of a tile cheaper than its gate, so more warps gate.
 // ASM  : kpad > 768: a 128-query block no longer fits TMEM next to an accumulator, so the A operand
 //        is streamed by TMA with the rows (one 16 KB A block + one 16 KB B block per stage, both
-//        128B-swizzled K-major) and the MMAs take both operands from shared memory. The smem fill
-//        rate this needs (128 B/clk at full tensor rate) is about twice what an SM gets from L2,
-//        so this variant is L2-bandwidth-bound at roughly half the tensor roofline.
-template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+//        128B-swizzled K-major) and the MMAs take both operands from shared memory (bound by the
+//        L2 -> SM fill rate at about 0.7 of the tensor roofline).
+// BN   : database rows per tile (UMMA N). 128, or 64 for kpad in {640, 768}: with the 384-column A
+//        operand only 128 TMEM columns are left, and ONE 128-column accumulator makes the MMA wait
+//        while the epilogue pulls every finished tile out of TMEM (~12 % of the tile time). Two
+//        64-column accumulators restore the overlap; a stage then holds 64 rows x 128 K (two TMA
+//        boxes), so the MMA warp still issues 8 instructions per barrier round trip.
+template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 struct FilterCfg {
-  static constexpr int STAGE_BYTES = ASM ? 2 * (TF_BM * TF_BK * 2) : (TF_BM * TF_BK * 2);
+  static constexpr int KSTEP = (BN == 64) ? 128 : 64;              // K elements per stage
+  static constexpr int B_BYTES = BN * KSTEP * 2;                    // 16 KB either way
+  static constexpr int STAGE_BYTES = (ASM ? TF_BM * TF_BK * 2 : 0) + B_BYTES;
   static constexpr int STAGES = ASM ? (KP > 16 ? 5 : 6) : 10;
+  static_assert(!ASM || BN == 128, "the streamed-A variant uses 128-row tiles");
 };
 
-template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 __global__ void __launch_bounds__(64 + 128 * EW, 1)
     tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a, FilterArgs a) {
-  constexpr int TF_STAGES = FilterCfg<KP, NBUF, EW, DBG, ASM>::STAGES;
-  constexpr int TF_STAGE_BYTES = FilterCfg<KP, NBUF, EW, DBG, ASM>::STAGE_BYTES;
+  using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
+  constexpr int TF_BN = BN;
+  constexpr int TF_STAGES = Cfg::STAGES;
+  constexpr int TF_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int KSTEP = Cfg::KSTEP;
   constexpr int TF_B_OFF = ASM ? (TF_BM * TF_BK * 2) : 0;  // B block within a stage (A block first when streamed)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve-up: [B stages][cand_row 128*EW*KP][queue 2*16*128*EW][aux 2*BN][barriers][tmem ptr]
@@ -175,7 +184,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t KB = a.kpad / TF_BK;
+  const uint32_t KB = a.kpad / KSTEP;   // stages per tile
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TF_STAGES; ++i) {
@@ -216,7 +225,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           if (elect_one()) {
             mbar_expect_tx(full + stage, TF_STAGE_BYTES);
             if (ASM) tma_load_2d(sb + stage * TF_STAGE_BYTES, &tmap_a, full + stage, (int)(kb * TF_BK), (int)(qblk * TF_BM));
-            tma_load_2d(sb + stage * TF_STAGE_BYTES + TF_B_OFF, &tmap_b, full + stage, (int)(kb * TF_BK), (int)(t * TF_BN));
+#pragma unroll
+            for (int h = 0; h < KSTEP / TF_BK; ++h)  // one 128-byte-wide box per 64 K elements
+              tma_load_2d(sb + stage * TF_STAGE_BYTES + TF_B_OFF + h * (TF_BN * TF_BK * 2), &tmap_b, full + stage,
+                          (int)(kb * KSTEP + h * TF_BK), (int)(t * TF_BN));
           }
           __syncwarp();
           if (++stage == TF_STAGES) {
@@ -253,13 +265,14 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           if (elect_one()) {
             const uint64_t adesc = bdesc0 + (uint64_t)(stage * (TF_STAGE_BYTES >> 4));
             const uint64_t bdesc = adesc + (uint64_t)(TF_B_OFF >> 4);
-            const uint32_t a_col = tmem_a + kb * (TF_BK / 2);
+            const uint32_t a_col = tmem_a + kb * (KSTEP / 2);
 #pragma unroll
-            for (uint32_t k = 0; k < TF_BK / 16; ++k) {
+            for (uint32_t k = 0; k < KSTEP / 16; ++k) {
               // A: 16 bf16 of K = 8 TMEM columns (or 32 bytes along the swizzled smem row);
-              // B: 32 bytes further along the swizzled row
-              if (ASM) tc_mma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-              else tc_mma_ts(d_tmem, a_col + k * 8, bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              // B: 32 bytes further along the swizzled row, next 64-K box after four steps
+              const uint64_t boff = (uint64_t)((k >> 2) * ((TF_BN * TF_BK * 2) >> 4) + (k & 3) * 2);
+              if (ASM) tc_mma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + boff, idesc, (kb | k) != 0);
+              else tc_mma_ts(d_tmem, a_col + k * 8, bdesc + boff, idesc, (kb | k) != 0);
             }
             tc_commit(empty + stage);                     // smem slot free once these MMAs retire
             if (kb == KB - 1) tc_commit(acc_full + buf);  // accumulator ready for the epilogue
@@ -628,13 +641,13 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms) {
   return 1;
 }
 
-template <int KP, int NBUF, int EW, bool DBG, bool ASM>
+template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream) {
-  using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM>;
+  using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
-                (size_t)2 * TF_BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
-  SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM>), smem);
-  tensor_filter_kernel<KP, NBUF, EW, DBG, ASM><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
+                (size_t)2 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
+  SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>), smem);
+  tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -645,7 +658,9 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
-  const uint32_t BN = TF_BN;
+  // 64-row tiles with two accumulators where one 128-column accumulator is all that fits next to A
+  const bool half_tiles = (s->kpad == 640 || s->kpad == 768) && !dbg_scores && s->opt_tensor_bn != 128;
+  const uint32_t BN = half_tiles ? 64u : 128u;
   const uint32_t n_rows = (uint32_t)s->rows;
   const uint32_t n_tiles = (n_rows + BN - 1) / BN;
   const uint32_t n_qb = (uint32_t)((nq + TF_BM - 1) / TF_BM);
@@ -735,18 +750,21 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   const bool two_buf = s->kpad <= 512;
   int32_t rc;
   if (stream_a) {
-    if (dbg_scores) rc = launch_filter<16, 2, 1, true, true>(tmap, tmap_a, fa, grid, stream);
-    else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true>(tmap, tmap_a, fa, grid, stream)
-                             : launch_filter<32, 2, 1, false, true>(tmap, tmap_a, fa, grid, stream);
+    if (dbg_scores) rc = launch_filter<16, 2, 1, true, true, 128>(tmap, tmap_a, fa, grid, stream);
+    else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream)
+                             : launch_filter<32, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream);
   } else if (dbg_scores) {
-    rc = two_buf ? launch_filter<16, 2, 1, true, false>(tmap, tmap_a, fa, grid, stream)
-                 : launch_filter<16, 1, 1, true, false>(tmap, tmap_a, fa, grid, stream);
+    rc = two_buf ? launch_filter<16, 2, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream)
+                 : launch_filter<16, 1, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream);
+  } else if (half_tiles) {
+    rc = (kprime == 16) ? launch_filter<16, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream)
+                        : launch_filter<32, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream);
   } else if (ew == 1) {
-    rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false>(tmap, tmap_a, fa, grid, stream)
-                        : launch_filter<32, 1, 1, false, false>(tmap, tmap_a, fa, grid, stream);
+    rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream)
+                        : launch_filter<32, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream);
   } else {
-    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false>(tmap, tmap_a, fa, grid, stream)
-                        : launch_filter<32, 2, 2, false, false>(tmap, tmap_a, fa, grid, stream);
+    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream)
+                        : launch_filter<32, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream);
   }
   if (prof) prof->end();
   SCN_TRY(rc);
