@@ -131,6 +131,7 @@ struct FilterArgs {
   uint32_t* cand_row;       // [nq][n_chunks][KP]
   float* chunk_tau;         // [nq][n_chunks]
   float* dbg_scores;        // optional [nq][n_rows]
+  uint32_t* hint;           // [nq] ord(best threshold any finished list of the query has reached), 0xFFFFFFFF = none
 };
 
 
@@ -324,7 +325,19 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         sc[j] = INF;
         my_row[j * ET] = ROW_NONE;
       }
-      float theta = INF;   // max of sc[] == the KP-th best score seen so far
+      // Admission threshold. A list that has finished publishes its final threshold (its KP-th best
+      // score): the query's overall KP-th best can only be lower, so that value is a valid starting
+      // threshold for every other list of the same query — rows it rejects could never have made
+      // the final cut, and `theta` stays a lower bound on the score of every rejected row, which is
+      // all the certificate needs. Lists of later waves therefore admit only a handful of rows
+      // instead of re-converging from +Inf (KP*ln(rows/KP) insertions each).
+      float hint = INF;
+      if (a.hint && q_global < a.nq) {
+        uint32_t h;
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(h) : "l"(a.hint + q_global));
+        if (h != 0xFFFFFFFFu) hint = ord_f32(h);
+      }
+      float theta = hint;  // min(hint, max of sc[]): the threshold every admitted row must beat
       int imax = 0;        // a slot holding theta
       // additive per-column term for the first tile, fetched one tile ahead from here on
       float aux_next = INF;
@@ -413,7 +426,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
                   mi[t2] = gt ? mi[t2 + w] : mi[t2];
                 }
               }
-              theta = mv[0];
+              theta = fminf(mv[0], hint);
               imax = mi[0];
             }
           }
@@ -441,6 +454,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           a.cand_row[base + j] = my_row[j * ET];
         }
         a.chunk_tau[(size_t)q_global * a.n_chunks * EW + vchunk] = theta;
+        if (a.hint && theta < INF) atomicMin(a.hint + q_global, f32_ord(theta));
       }
       // all MMAs of this item have retired (the last acc_full was waited on), so A may be rewritten
     }
@@ -713,6 +727,9 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(scratch.alloc(&d_fail, nq));
   SCN_TRY(scratch.alloc(&d_fail2, nq));
   SCN_TRY(scratch.alloc(&d_nfail, 2));
+  uint32_t* d_hint = nullptr;
+  SCN_TRY(scratch.alloc(&d_hint, nq));
+  SCN_CUDA(cudaMemsetAsync(d_hint, 0xFF, nq * sizeof(uint32_t), stream));
   SCN_CUDA(cudaMemsetAsync(d_nfail, 0, 2 * sizeof(uint32_t), stream));
 
   if (prof) prof->begin("prep_queries");
@@ -745,6 +762,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   fa.cand_row = d_crow;
   fa.chunk_tau = d_ctau;
   fa.dbg_scores = dbg_scores;
+  fa.hint = s->opt_tensor_hint ? d_hint : nullptr;
   int grid = (int)std::min<uint32_t>((uint32_t)sms, n_qb * n_chunks);
   if (prof) prof->begin("tensor_filter");
   const bool two_buf = s->kpad <= 512;

@@ -587,6 +587,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_min_batch = value;
   } else if (n == "overfetch") {
     s->opt_overfetch = value;
+  } else if (n == "tensor_hint") {
+    s->opt_tensor_hint = value;
   } else if (n == "tensor_bn") {
     s->opt_tensor_bn = value;
   } else if (n == "tensor_chunks") {

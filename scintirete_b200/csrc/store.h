@@ -62,6 +62,7 @@ struct scn_store {
   int64_t opt_flat_path = 0;
   int64_t opt_tensor_min_batch = 1;  // the bf16 filter streams half the bytes of the fp32 scan: it wins at every batch size
   int64_t opt_overfetch = 0;  // 0 = auto
+  int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
   int64_t opt_profile = 0;
