@@ -223,6 +223,42 @@ __device__ __forceinline__ float exact_norm_thread(const float* __restrict__ v, 
   return __fsqrt_rn(s);
 }
 
+// Same value from a zero-padded, 16-byte-aligned copy (n4 float4s): the +0 terms of the padding do
+// not change the sum, 128-bit loads run ahead of the dependent add chain.
+__device__ __forceinline__ float exact_norm_padded(const float* __restrict__ v, uint32_t n4) {
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  float s = 0.0f;
+#pragma unroll 8
+  for (uint32_t i = 0; i < n4; ++i) {
+    const float4 a = v4[i];
+    s = __fadd_rn(s, __fmul_rn(a.x, a.x));
+    s = __fadd_rn(s, __fmul_rn(a.y, a.y));
+    s = __fadd_rn(s, __fmul_rn(a.z, a.z));
+    s = __fadd_rn(s, __fmul_rn(a.w, a.w));
+  }
+  return __fsqrt_rn(s);
+}
+
+// Block-cooperative copy of a query row into a zero-padded shared-memory buffer: eight independent
+// loads per thread are in flight before the first store (a plain load->store loop serialises one
+// memory latency per element and thread).
+__device__ __forceinline__ void stage_query(float* __restrict__ dst, const float* __restrict__ src, uint32_t dim, uint32_t pitch,
+                                            uint32_t tid, uint32_t nthreads) {
+  for (uint32_t i0 = tid; i0 < pitch; i0 += 8 * nthreads) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t i = i0 + u * nthreads;
+      t[u] = (i < dim) ? __ldg(src + i) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t i = i0 + u * nthreads;
+      if (i < pitch) dst[i] = t[u];
+    }
+  }
+}
+
 __device__ __forceinline__ bool bit_test(const uint32_t* __restrict__ bits, uint32_t i) {
   return (__ldg(bits + (i >> 5)) >> (i & 31)) & 1u;
 }

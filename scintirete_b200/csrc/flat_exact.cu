@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ v
   for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
     const uint32_t qi = qlist ? qlist[slot] : slot;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < pitch; i += blockDim.x) s_q[i] = (i < dim) ? q[(size_t)qi * dim + i] : 0.0f;
+    stage_query(s_q, q + (size_t)qi * dim, dim, pitch, threadIdx.x, blockDim.x);
     __syncthreads();
-    if (METRIC == M_COS && threadIdx.x == 0) s_qnorm = exact_norm_thread(s_q, dim);
+    if (METRIC == M_COS && threadIdx.x == 0) s_qnorm = exact_norm_padded(s_q, pitch / 4);
     __syncthreads();
     for (uint32_t c = threadIdx.x; c < ncand_pad; c += blockDim.x) {
       uint64_t key = KEY_NONE;

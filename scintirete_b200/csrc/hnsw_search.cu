@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
   for (uint32_t qslot = warp_global; qslot < nq; qslot += warps_total) {
     const uint32_t qi = a.qlist ? a.qlist[qslot] : qslot;
     __syncwarp();
-    for (uint32_t i = lane; i < a.pitch; i += 32) sq[i] = (i < a.dim) ? a.q[(size_t)qi * a.dim + i] : 0.0f;
+    stage_query(sq, a.q + (size_t)qi * a.dim, a.dim, a.pitch, lane, 32);
     for (uint32_t i = lane; i < n_groups; i += 32) reinterpret_cast<uint4*>(hash)[i] = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
     __syncwarp();
     float qn = 0.0f;
     if (METRIC == M_COS) {
-      if (lane == 0) qn = exact_norm_thread(sq, a.dim);
+      if (lane == 0) qn = exact_norm_padded(sq, a.pitch / 4);
       qn = __shfl_sync(0xffffffffu, qn, 0);
     }
 
