@@ -139,7 +139,8 @@ __device__ __forceinline__ float exact_acc_thread(const float* __restrict__ q, c
 // buffered in registers, so 16-32 independent 128-bit loads per lane (up to 16 KB per warp) are in
 // flight before the first dependent add: a 512-byte row costs one memory latency instead of the
 // eight that a 4-wide unrolled loop serialises.
-constexpr int DCH = 16;  // float4 per register chunk
+// DCH = float4 per register chunk: 16 (two chunks = 128 data registers, one memory latency per
+// 512-byte row; HNSW traversal) or 8 (half the registers, more resident warps; rerank).
 
 // 256-bit read-only load (rows are 32-byte aligned: pitch is a multiple of 8 floats). One lane
 // reads one row, so a warp-wide load touches up to 32 different lines and L1 spends a tag cycle on
@@ -156,7 +157,7 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
 
 // FULL: the chunk lies entirely inside the row -> straight-line code without predicates, so the
 // scheduler can hoist the query LDS ahead of the dependent add chain.
-template <bool FULL>
+template <bool FULL, int DCH>
 __device__ __forceinline__ void load_chunk(float4 (&b)[DCH], const float4* __restrict__ x4, uint32_t c, uint32_t pitch4) {
 #pragma unroll
   for (int i = 0; i < DCH; i += 2) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void load_chunk(float4 (&b)[DCH], const float4* __res
   }
 }
 
-template <int METRIC, bool FULL>
+template <int METRIC, bool FULL, int DCH>
 __device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], const float4* __restrict__ q4, uint32_t c, uint32_t pitch4) {
   float4 qa[DCH];
 #pragma unroll
@@ -184,7 +185,7 @@ __device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], co
   return acc;
 }
 
-template <int METRIC>
+template <int METRIC, int DCH = 16>
 __device__ __forceinline__ float row_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
                                               const float* sq, float qn, uint32_t row) {
   const float4* x4 = reinterpret_cast<const float4*>(vec + (size_t)row * pitch);
@@ -194,23 +195,23 @@ __device__ __forceinline__ float row_distance(const float* __restrict__ vec, con
   float4 b0[DCH], b1[DCH];
   float xn = 0.0f;
   float acc = 0.0f;
-  if (nfull > 0) load_chunk<true>(b0, x4, 0, pitch4);
-  if (nfull > 1) load_chunk<true>(b1, x4, 1, pitch4);
+  if (nfull > 0) load_chunk<true, DCH>(b0, x4, 0, pitch4);
+  if (nfull > 1) load_chunk<true, DCH>(b1, x4, 1, pitch4);
   if (METRIC == M_COS) xn = __ldg(norm + row);
   uint32_t c = 0;
   for (; c + 1 < nfull; c += 2) {
-    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
-    if (c + 2 < nfull) load_chunk<true>(b0, x4, c + 2, pitch4);
-    acc = acc_chunk<METRIC, true>(acc, b1, q4, c + 1, pitch4);
-    if (c + 3 < nfull) load_chunk<true>(b1, x4, c + 3, pitch4);
+    acc = acc_chunk<METRIC, true, DCH>(acc, b0, q4, c, pitch4);
+    if (c + 2 < nfull) load_chunk<true, DCH>(b0, x4, c + 2, pitch4);
+    acc = acc_chunk<METRIC, true, DCH>(acc, b1, q4, c + 1, pitch4);
+    if (c + 3 < nfull) load_chunk<true, DCH>(b1, x4, c + 3, pitch4);
   }
   if (c < nfull) {  // odd number of full chunks: the last one sits in b0
-    acc = acc_chunk<METRIC, true>(acc, b0, q4, c, pitch4);
+    acc = acc_chunk<METRIC, true, DCH>(acc, b0, q4, c, pitch4);
     ++c;
   }
   if (c * DCH < pitch4) {  // ragged tail (< 16 float4)
-    load_chunk<false>(b1, x4, c, pitch4);
-    acc = acc_chunk<METRIC, false>(acc, b1, q4, c, pitch4);
+    load_chunk<false, DCH>(b1, x4, c, pitch4);
+    acc = acc_chunk<METRIC, false, DCH>(acc, b1, q4, c, pitch4);
   }
   return finish_distance<METRIC>(acc, qn, xn);
 }

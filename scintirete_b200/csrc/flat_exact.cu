@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ v
       if (c < ncand) {
         uint32_t row = cand[(size_t)qi * ncand + c];
         if (row < n_rows && !bit_test(deleted, row)) {
-          const float d = row_distance<METRIC>(vec, norm, pitch, s_q, METRIC == M_COS ? s_qnorm : 0.0f, row);
+          const float d = row_distance<METRIC, 8>(vec, norm, pitch, s_q, METRIC == M_COS ? s_qnorm : 0.0f, row);
           key = make_key(d, row + row_base);
         }
       }
