@@ -351,6 +351,10 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    for kv in args.opt:
+        name, val = kv.split("=")
+        store.set_option(name, int(val))
+
     # ---- timed region 1: device-resident queries -------------------------------------------------
     store.set_option("profile", 0)
     for _ in range(args.warmup):
@@ -487,6 +491,7 @@ def main():
     ap.add_argument("--nq", type=int)
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (scn_set_option), repeatable")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="row-shard exchange for --gpus > 1")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])

@@ -276,36 +276,100 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// ---- 1-D bulk copies (TMA engine) + mbarrier, for row gathers -----------------------------------
-// One lane asks for one contiguous piece of a row; the copy engine fetches it as ONE request, so
-// DRAM sees whole 512-byte bursts instead of 32-byte sectors interleaved with thousands of other
-// rows (which thrashes the DRAM row buffers: the lane-per-row LDG gather of 3 KB rows reached
-// 1.4 TB/s).
 __device__ __forceinline__ uint32_t cvta_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(bar)), "r"(count));
+
+// ---- warp gather: the reference's Distance(query, row) for up to 32 rows, one per lane ------------
+// The rows of a batch are copied into shared memory with warp-wide cp.async: ONE instruction moves
+// 512 contiguous bytes of ONE row (16 bytes per lane), so DRAM sees whole bursts and L1 spends four
+// tag cycles per 512 bytes. Each lane then walks its own row (stage rows GA_ROW bytes apart:
+// conflict-free LDS.128) in the reference's sequential fp32 order.
+// History (1 M x 128, ef = 128, 10 k queries): lane-per-row LDG.256 into registers 9.1 ms (32 lines
+// per instruction: L1-tag-bound, 253 registers); one 1-D bulk copy (UBLKCP) per lane and row 5.9 ms —
+// exactly the copy engine's request rate (one request per ~46 cycles and SM: 39.9 M requests / 148
+// SMs); warp-wide cp.async: see profiles/.
+// `stage` holds 2 x 32 x GA_ROW bytes (one buffer suffices when a row is a single piece).
+constexpr uint32_t GA_CHUNK = 512;
+constexpr uint32_t GA_ROW = GA_CHUNK + 16;
+
+// stage `ch` of the rows of all lanes in `mask` -> buffer ch & 1, one commit group
+__device__ __forceinline__ void gather_issue(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask, uint32_t ch,
+                                             unsigned char* stage, uint32_t lane) {
+  const uint32_t row_bytes = pitch * 4;  // multiple of 32
+  const uint32_t bytes = min(GA_CHUNK, row_bytes - ch * GA_CHUNK);
+  const bool mine = lane * 16 < bytes;
+  const uint32_t dst0 = cvta_smem(stage + (ch & 1) * 32 * GA_ROW + lane * 16);
+  const float* src0 = vec + (size_t)ch * (GA_CHUNK / 4) + lane * 4;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t r = __shfl_sync(0xffffffffu, row, i);
+    if (((mask >> i) & 1u) && mine)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + i * GA_ROW), "l"(src0 + (size_t)r * pitch) : "memory");
+  }
+  cp_async_commit();
 }
-__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cvta_smem(bar)), "r"(bytes) : "memory");
+// the first one or two stages of a gather (what fits the buffers); gather_finish issues the rest
+__device__ __forceinline__ void gather_begin(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask,
+                                             unsigned char* stage, uint32_t lane) {
+  gather_issue(vec, pitch, row, mask, 0, stage, lane);
+  if (pitch * 4 > GA_CHUNK) gather_issue(vec, pitch, row, mask, 1, stage, lane);
 }
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "BW_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra BD_%=;\n\t"
-      "bra BW_%=;\n\t"
-      "BD_%=:\n\t}" ::"r"(cvta_smem(bar)),
-      "r"(parity)
-      : "memory");
+// Completes a gather begun for a superset of the lanes in `mask` (lanes may have been dropped
+// since, e.g. rows found in the visited set while their copies were in flight: their data is
+// ignored, later stages are requested for the lanes of `mask` only). Returns +Inf on other lanes.
+template <int METRIC>
+__device__ __forceinline__ float gather_finish(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
+                                               const float* sq, float qn, uint32_t row, uint32_t mask, unsigned char* stage,
+                                               uint32_t lane) {
+  const uint32_t row_bytes = pitch * 4;
+  const uint32_t n_chunks = (row_bytes + GA_CHUNK - 1) / GA_CHUNK;
+  const bool valid = (mask >> lane) & 1u;
+  if (!mask) {  // nobody left: drain what was begun
+    cp_async_wait<0>();
+    __syncwarp();
+    return __int_as_float(0x7f800000);
+  }
+  float acc = 0.0f;
+  const float xn = (METRIC == M_COS && valid) ? __ldg(norm + row) : 0.0f;
+  for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+    if (ch + 1 < n_chunks) cp_async_wait<1>();  // stage ch + 1 may still be in flight
+    else cp_async_wait<0>();
+    __syncwarp();  // every lane's pieces of this stage have landed
+    const uint32_t n4 = min(GA_CHUNK, row_bytes - ch * GA_CHUNK) / 16;
+    if (valid) {
+      const float4* x4 = reinterpret_cast<const float4*>(stage + ((ch & 1) * 32 + lane) * GA_ROW);
+      const float4* q4 = reinterpret_cast<const float4*>(sq) + ch * (GA_CHUNK / 16);
+      if (n4 == GA_CHUNK / 16) {
+#pragma unroll
+        for (uint32_t i = 0; i < GA_CHUNK / 16; ++i) {
+          const float4 xa = x4[i], qa = q4[i];
+          acc = acc_step<METRIC>(acc, qa.x, xa.x);
+          acc = acc_step<METRIC>(acc, qa.y, xa.y);
+          acc = acc_step<METRIC>(acc, qa.z, xa.z);
+          acc = acc_step<METRIC>(acc, qa.w, xa.w);
+        }
+      } else {
+        for (uint32_t i = 0; i < n4; ++i) {
+          const float4 xa = x4[i], qa = q4[i];
+          acc = acc_step<METRIC>(acc, qa.x, xa.x);
+          acc = acc_step<METRIC>(acc, qa.y, xa.y);
+          acc = acc_step<METRIC>(acc, qa.z, xa.z);
+          acc = acc_step<METRIC>(acc, qa.w, xa.w);
+        }
+      }
+    }
+    __syncwarp();  // this buffer is free again
+    if (ch + 2 < n_chunks) gather_issue(vec, pitch, row, mask, ch + 2, stage, lane);
+  }
+  return valid ? finish_distance<METRIC>(acc, qn, xn) : __int_as_float(0x7f800000);
 }
-// size and both addresses must be multiples of 16 bytes
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cvta_smem(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(cvta_smem(bar))
-               : "memory");
+
+template <int METRIC>
+__device__ __forceinline__ float gather_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
+                                                 const float* sq, float qn, uint32_t row, uint32_t mask, unsigned char* stage,
+                                                 uint32_t lane) {
+  gather_begin(vec, pitch, row, mask, stage, lane);
+  return gather_finish<METRIC>(vec, norm, pitch, sq, qn, row, mask, stage, lane);
 }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 inline uint32_t next_pow2(uint32_t v) {

@@ -355,15 +355,13 @@ int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64
 
 // ---- K3: exact rerank of gathered candidate rows ------------------------------------------------
 // One warp per query. Candidates are taken 32 at a time, one row per lane. Rows arrive in
-// shared memory through 1-D bulk copies (each lane requests 512 contiguous bytes of its row per
-// stage, two stages in flight), then every lane walks its own row in the reference's sequential
+// shared memory through warp-wide cp.async (one instruction = 512 contiguous bytes of one row, two
+// stages in flight; common.cuh), then every lane walks its own row in the reference's sequential
 // fp32 order (conflict-free LDS.128: rows are 528 bytes apart). The warp sorts the keys and emits
 // the first k distinct ones.
-constexpr uint32_t RR_CHUNK = 512;              // bytes of a row per stage
-constexpr uint32_t RR_ROW = RR_CHUNK + 16;      // smem distance between rows of a stage
 
 __host__ __device__ inline size_t rerank_smem_bytes(uint32_t pitch, uint32_t ncand_pad) {
-  return (size_t)pitch * 4 + (size_t)ncand_pad * 8 + 2 * 32 * RR_ROW + 2 * 8;
+  return (size_t)pitch * 4 + (size_t)ncand_pad * 8 + 2 * 32 * GA_ROW;
 }
 
 template <int METRIC>
@@ -377,18 +375,8 @@ __global__ void __launch_bounds__(32) rerank_kernel(const float* __restrict__ ve
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);                                   // [pitch]
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q + pitch);                       // [ncand_pad]
-  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_keys + ncand_pad);     // [2][32][RR_ROW]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + 2 * 32 * RR_ROW);          // [2]
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_keys + ncand_pad);     // [2][32][GA_ROW]
   const uint32_t lane = threadIdx.x;
-  const uint32_t row_bytes = pitch * 4;                                              // multiple of 32
-  const uint32_t n_chunks = (row_bytes + RR_CHUNK - 1) / RR_CHUNK;
-  if (lane == 0) {
-    bar_init(s_bar + 0, 1);
-    bar_init(s_bar + 1, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  uint32_t phase0 = 0, phase1 = 0;   // parities of the two stage barriers
   const uint32_t n_slots = nq_dev ? min(*nq_dev, nq) : nq;
   for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
     const uint32_t qi = qlist ? qlist[slot] : slot;
@@ -408,59 +396,11 @@ __global__ void __launch_bounds__(32) rerank_kernel(const float* __restrict__ ve
         if (row >= n_rows || bit_test(deleted, row)) row = ROW_NONE;
       }
       const bool valid = row != ROW_NONE;
-      const uint32_t n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+      const uint32_t mask = __ballot_sync(0xffffffffu, valid);
       uint64_t key = KEY_NONE;
-      if (n_valid) {
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(vec + (size_t)row * pitch);
-        // issue stage `ch` (chunk index) into buffer ch & 1
-        auto issue = [&](uint32_t ch) {
-          const uint32_t bytes = min(RR_CHUNK, row_bytes - ch * RR_CHUNK);
-          uint64_t* bar = s_bar + (ch & 1);
-          if (lane == 0) bar_expect_tx(bar, bytes * n_valid);
-          __syncwarp();
-          if (valid) bulk_copy_g2s(s_stage + ((ch & 1) * 32 + lane) * RR_ROW, src + (size_t)ch * RR_CHUNK, bytes, bar);
-        };
-        issue(0);
-        if (n_chunks > 1) issue(1);
-        float acc = 0.0f;
-        const float xn = (METRIC == M_COS && valid) ? __ldg(norm + row) : 0.0f;
-        for (uint32_t ch = 0; ch < n_chunks; ++ch) {
-          if (ch & 1) {
-            bar_wait(s_bar + 1, phase1);
-            phase1 ^= 1;
-          } else {
-            bar_wait(s_bar + 0, phase0);
-            phase0 ^= 1;
-          }
-          const uint32_t n4 = min(RR_CHUNK, row_bytes - ch * RR_CHUNK) / 16;
-          if (valid) {
-            const float4* x4 = reinterpret_cast<const float4*>(s_stage + ((ch & 1) * 32 + lane) * RR_ROW);
-            const float4* q4 = reinterpret_cast<const float4*>(s_q) + ch * (RR_CHUNK / 16);
-            if (n4 == RR_CHUNK / 16) {
-#pragma unroll
-              for (uint32_t i = 0; i < RR_CHUNK / 16; ++i) {
-                const float4 xa = x4[i], qa = q4[i];
-                acc = acc_step<METRIC>(acc, qa.x, xa.x);
-                acc = acc_step<METRIC>(acc, qa.y, xa.y);
-                acc = acc_step<METRIC>(acc, qa.z, xa.z);
-                acc = acc_step<METRIC>(acc, qa.w, xa.w);
-              }
-            } else {
-              for (uint32_t i = 0; i < n4; ++i) {
-                const float4 xa = x4[i], qa = q4[i];
-                acc = acc_step<METRIC>(acc, qa.x, xa.x);
-                acc = acc_step<METRIC>(acc, qa.y, xa.y);
-                acc = acc_step<METRIC>(acc, qa.z, xa.z);
-                acc = acc_step<METRIC>(acc, qa.w, xa.w);
-              }
-            }
-          }
-          // this buffer is free again: order the generic-proxy reads before the next async write
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (ch + 2 < n_chunks) issue(ch + 2);
-        }
-        if (valid) key = make_key(finish_distance<METRIC>(acc, qnorm, xn), row + row_base);
+      if (mask) {
+        const float d = gather_distance<METRIC>(vec, norm, pitch, s_q, qnorm, row, mask, s_stage, lane);
+        if (valid) key = make_key(d, row + row_base);
       }
       s_keys[c] = key;
     }

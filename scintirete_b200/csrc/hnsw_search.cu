@@ -32,7 +32,7 @@
 
 namespace scn {
 
-constexpr int HNSW_WARPS = 2;
+constexpr int HNSW_MAX_WARPS = 2;  // warps (= queries) per CTA: 2 for the register gather, 1 for the shared-memory gather
 constexpr uint32_t HASH_EMPTY = 0u;
 
 struct HnswArgs {
@@ -47,15 +47,19 @@ struct HnswArgs {
   uint32_t pitch, dim, n_rows;
   uint32_t s0, su;
   uint32_t has_deleted;    // 0: no row is soft-deleted, the bitmap need not be read
+  uint32_t global_first;   // 1: the first pass keeps its visited tables in global memory too (L2-resident; more warps per SM)
+  uint32_t early_issue;    // shared-memory gather: request the rows of a list before the visited test
+  uint32_t stages;         // shared-memory gather: stage buffers per warp (1 when a row is one 512-byte piece, else 2)
   uint32_t entry_row;
   int32_t max_layer;
   const float* q;
   const uint32_t* qlist;   // optional list of query indices (overflow pass)
   uint32_t* nq_dev;        // optional device count for qlist
   uint32_t nq, k, ef, ef_pad;
+  uint32_t max_per_sm;     // global_first: cap on resident CTAs per SM (0 = whatever fits)
   uint32_t hash_size;      // entries per warp
   uint32_t* ghash;         // global tables [warps][hash_size] when USE_GLOBAL
-  uint32_t* overflow_list; // queries whose visited table overflowed (smem pass)
+  uint32_t* overflow_list; // first pass: queries whose visited table overflowed (nullptr in the overflow pass)
   uint32_t* overflow_count;
   uint64_t* out_ids;
   float* out_dist;
@@ -63,10 +67,15 @@ struct HnswArgs {
   unsigned long long* stats;  // [0] distance evaluations, [1] expansions (optional)
 };
 
-__host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t hash_size, bool global_hash) {
-  // wkey[2][ef_pad] u64 | snk[32] u64 | q[pitch] f32 | wrow[2][ef_pad] u32 | snr[32] u32 | hash
-  return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + (global_hash ? 0 : (size_t)hash_size * 4);
+__host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t hash_size, bool global_hash,
+                                                  uint32_t stages) {
+  // wkey[2][ef_pad] u64 | snk[32] u64 | q[pitch] f32 | wrow[2][ef_pad] u32 | snr[32] u32 |
+  // stage[stages][32][GA_ROW] (shared-memory gather only) | hash
+  return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + (size_t)stages * 32 * GA_ROW +
+         (global_hash ? 0 : (size_t)hash_size * 4);
 }
+
+__device__ __forceinline__ uint32_t home_group(uint32_t row, uint32_t n_groups) { return __umulhi(row * 2654435761u, n_groups); }
 
 // visited set: open addressing over groups of four 32-bit slots (one 128-bit load per probe). Slots
 // of a group fill in order and are never emptied within a query, so a group that still has an
@@ -76,7 +85,8 @@ template <bool GLOBAL>
 __device__ __forceinline__ uint4 ld_group(const uint32_t* p) {
   uint4 v;
   if (GLOBAL) {
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    // (the table is private to one warp, written with L2 atomics: only L1 must be bypassed)
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   } else {
     asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
@@ -87,7 +97,7 @@ __device__ __forceinline__ uint4 ld_group(const uint32_t* p) {
 
 template <bool GLOBAL>
 __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups, uint32_t row) {
-  uint32_t g = __umulhi(row * 2654435761u, n_groups);
+  uint32_t g = home_group(row, n_groups);
   const uint32_t key = row + 1;
   for (uint32_t probes = 0; probes <= n_groups;) {
     uint32_t* grp = tab + g * 4;
@@ -106,13 +116,55 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups,
   return false;  // table full (guarded against by the overflow check)
 }
 
-template <int METRIC, bool USE_GLOBAL>
-__global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
+// Warp-collective insert for a table in GLOBAL memory, where every dependent access is an L2 round
+// trip: one group load per probe round and NO atomic. The table is private to the warp, so the
+// lanes settle among themselves who takes which slot (match.any on the group index: the lanes
+// that want a slot of the same group take consecutive ones, those that do not fit move on to the
+// next group in the next round) and write with plain stores, which nobody waits for. `pre` may hold
+// the home group fetched ahead of time (valid only if nothing was inserted since). Lanes with
+// want == false only take part in the collectives. Returns true on a first visit.
+__device__ __forceinline__ bool visited_insert_warp(uint32_t* tab, uint32_t n_groups, uint32_t row, bool want, bool have_pre,
+                                                    uint4 pre, uint32_t lane) {
+  const uint32_t key = row + 1;
+  const uint32_t lt = (1u << lane) - 1u;
+  // the same row twice in one batch: the first lane inserts, the others see it as visited
+  const uint32_t same = __match_any_sync(0xffffffffu, key) & __ballot_sync(0xffffffffu, want);
+  bool pending = want && !(same & lt);
+  bool fresh = false;
+  uint32_t g = home_group(row, n_groups);
+  for (uint32_t round = 0; round <= n_groups; ++round) {
+    if (!__any_sync(0xffffffffu, pending)) break;
+    int e = 4;
+    if (pending) {
+      const uint4 v = (have_pre && round == 0) ? pre : ld_group<true>(tab + g * 4);
+      if (v.x == key || v.y == key || v.z == key || v.w == key) pending = false;
+      else e = (v.x == HASH_EMPTY) ? 0 : (v.y == HASH_EMPTY) ? 1 : (v.z == HASH_EMPTY) ? 2 : (v.w == HASH_EMPTY) ? 3 : 4;
+    }
+    const bool ins = pending && e < 4;
+    const uint32_t peers = __match_any_sync(0xffffffffu, g) & __ballot_sync(0xffffffffu, ins);
+    if (pending) {
+      const uint32_t slot = (uint32_t)e + __popc(peers & lt);
+      if (slot < 4) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(tab + g * 4 + slot), "r"(key) : "memory");
+        pending = false;
+        fresh = true;
+      } else if (++g == n_groups) {
+        g = 0;
+      }
+    }
+    __syncwarp();  // this round's stores are ordered before the next round's (and the next batch's) loads
+  }
+  return fresh;
+}
+
+template <int METRIC, bool USE_GLOBAL, bool GATHER>
+__global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
   extern __shared__ __align__(16) unsigned char smem_hnsw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t warp_global = blockIdx.x * HNSW_WARPS + warp;
-  const uint32_t warps_total = gridDim.x * HNSW_WARPS;
-  unsigned char* base = smem_hnsw + hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, USE_GLOBAL) * warp;
+  const uint32_t block_warps = blockDim.x >> 5;
+  const uint32_t warp_global = blockIdx.x * block_warps + warp;
+  const uint32_t warps_total = gridDim.x * block_warps;
+  unsigned char* base = smem_hnsw + hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, USE_GLOBAL, GATHER ? a.stages : 0) * warp;
   uint64_t* wkey0 = reinterpret_cast<uint64_t*>(base);
   uint64_t* wkey1 = wkey0 + a.ef_pad;
   uint64_t* snk = wkey1 + a.ef_pad;                              // sorted new keys
@@ -120,7 +172,9 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
   uint32_t* wrow0 = reinterpret_cast<uint32_t*>(sq + a.pitch);
   uint32_t* wrow1 = wrow0 + a.ef_pad;
   uint32_t* snr = wrow1 + a.ef_pad;                              // rows of the sorted new keys
-  uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : (snr + 32);
+  unsigned char* stage = reinterpret_cast<unsigned char*>(snr + 32);
+  uint32_t* smem_hash = reinterpret_cast<uint32_t*>(stage + (GATHER ? (size_t)a.stages * 32 * GA_ROW : 0));
+  uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : smem_hash;
   const uint32_t ef = a.ef;
   const uint32_t n_groups = a.hash_size >> 2;  // hash_size is a multiple of 4
   const uint32_t nq = a.qlist ? min(*a.nq_dev, a.nq) : a.nq;
@@ -165,12 +219,15 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
       uint32_t p_lo = 0;               // beam: every entry of W before p_lo has been expanded
       uint32_t pre_row = ROW_NONE;     // beam: adjacency prefetched for this row (the runner-up)
       uint32_t pre_nb = ROW_NONE;
+      uint32_t pre_grp_row = ROW_NONE; // global table: home groups of pre_nb fetched for this row, after the last insert
+      uint4 pre_grp = make_uint4(0, 0, 0, 0);
       for (;;) {
         // ================= produce: the next non-empty batch of rows, or the end =================
         uint32_t nb = ROW_NONE;
         bool ok = false;
         uint32_t mask = 0;
         bool finished = false;
+        bool begun = false;  // shared-memory gather: the copies of this batch are already in flight
         for (;;) {
           if (phase == PH_ENTRY) {
             nb = cur;
@@ -253,13 +310,35 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
             nb = (c0 + lane < list_len) ? __ldg(list + c0 + lane) : ROW_NONE;
           }
           ok = (nb != ROW_NONE);
+          if (GATHER) {
+            // Ask for the rows of ALL listed neighbours before the visited test: the copies then fly
+            // while the table is probed (two dependent round trips when it lives in global
+            // memory). Rows that turn out to be visited or deleted (about one in five) were
+            // fetched for nothing; bandwidth is not what bounds the walk.
+            const uint32_t listed = __ballot_sync(0xffffffffu, ok);
+            if (listed && a.early_issue) {
+              gather_begin(a.vec, a.pitch, nb, listed, stage, lane);
+              begun = true;
+            }
+          }
           // reference order: visited? -> deleted? -> mark visited. A deleted row is never
           // inserted, so testing `deleted` first and inserting only live rows is equivalent.
           if (ok && a.has_deleted) ok = !bit_test(a.deleted, nb);
-          if (ok) ok = visited_insert<USE_GLOBAL>(hash, n_groups, nb);
+          if (USE_GLOBAL) ok = visited_insert_warp(hash, n_groups, nb, ok, c0 == 0 && cur == pre_grp_row, pre_grp, lane);
+          else if (ok) ok = visited_insert<false>(hash, n_groups, nb);
           mask = __ballot_sync(0xffffffffu, ok);
           const uint32_t ns = __popc(mask);
+          if (USE_GLOBAL && c0 + 32 >= list_len) {
+            // nothing is inserted any more before the next expansion: if that is the runner-up, its
+            // probes can start from these group snapshots (off the critical path)
+            pre_grp_row = pre_row;
+            if (pre_row != ROW_NONE && pre_nb != ROW_NONE) pre_grp = ld_group<true>(hash + home_group(pre_nb, n_groups) * 4);
+          }
           if (!ns) {  // nothing new in this chunk
+            if (GATHER && begun) {  // drain the copies
+              gather_finish<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb, 0u, stage, lane);
+              begun = false;
+            }
             c0 += 32;
             if (c0 >= list_len) in_list = false;
             continue;
@@ -271,8 +350,14 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
         if (finished) break;
 
         // ================= evaluate: the reference's Distance(), one row per lane ================
+        // (register gather: 2 x 8 LDG.256 per lane in flight; shared-memory gather: one 512-byte request
+        // per row and stage to the copy engine, rows land in shared memory)
         float d = INF;
-        if (ok) d = row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb);
+        if (GATHER) {
+          if (!begun) gather_begin(a.vec, a.pitch, nb, mask, stage, lane);
+          d = gather_finish<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
+        }
+        else if (ok) d = row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb);
 
         // ================= consume ==============================================================
         if (phase == PH_ENTRY) {
@@ -389,7 +474,7 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
       }
     }
 
-    if (overflow && !USE_GLOBAL) {
+    if (overflow && a.overflow_list) {
       if (lane == 0) {
         uint32_t slot = atomicAdd(a.overflow_count, 1u);
         a.overflow_list[slot] = qi;
@@ -418,37 +503,59 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(HnswArgs a
   }
 }
 
-template <int METRIC>
+template <int METRIC, bool GATHER>
 static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
-  // pass 1: shared-memory visited table
-  const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false) * HNSW_WARPS;
-  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, false>), smem);
-  int per_sm = 0;
-  SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false>, HNSW_WARPS * 32, smem));
-  if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
-  uint32_t blocks_needed = (a.nq + HNSW_WARPS - 1) / HNSW_WARPS;
-  int grid = (int)std::min<uint32_t>(blocks_needed, (uint32_t)(sms * per_sm));
+  // pass 1: shared-memory visited table (or, global_first, a table of the same size in global memory)
+  const int warps = GATHER ? 1 : HNSW_MAX_WARPS;
+  const uint32_t stages = GATHER ? a.stages : 0;
+  const uint32_t blocks_needed = (a.nq + warps - 1) / warps;
   SCN_TRY(scratch.alloc(&a.overflow_list, (size_t)a.nq));
   SCN_TRY(scratch.alloc(&a.overflow_count, 1));
   SCN_CUDA(cudaMemsetAsync(a.overflow_count, 0, sizeof(uint32_t), stream));
-  if (prof) prof->begin("hnsw_search");
-  hnsw_search_kernel<METRIC, false><<<grid, HNSW_WARPS * 32, smem, stream>>>(a);
-  SCN_LAUNCHED();
-  if (prof) prof->end();
+  if (!a.global_first) {
+    const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, stages) * warps;
+    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, false, GATHER>), smem);
+    int per_sm = 0;
+    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false, GATHER>, warps * 32, smem));
+    if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
+    const int grid = (int)std::min<uint32_t>(blocks_needed, (uint32_t)(sms * per_sm));
+    if (prof) prof->begin("hnsw_search");
+    hnsw_search_kernel<METRIC, false, GATHER><<<grid, warps * 32, smem, stream>>>(a);
+    SCN_LAUNCHED();
+    if (prof) prof->end();
+  } else {
+    const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
+    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GATHER>), smem);
+    int per_sm = 0;
+    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, true, GATHER>, warps * 32, smem));
+    if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
+    if (a.max_per_sm > 0) per_sm = std::min<int>(per_sm, (int)a.max_per_sm);
+    const int grid = (int)std::min<uint32_t>(blocks_needed, (uint32_t)(sms * per_sm));
+    SCN_TRY(scratch.alloc(&a.ghash, (size_t)grid * warps * a.hash_size));
+    if (prof) prof->begin("hnsw_search");
+    hnsw_search_kernel<METRIC, true, GATHER><<<grid, warps * 32, smem, stream>>>(a);
+    SCN_LAUNCHED();
+    if (prof) prof->end();
+  }
   // pass 2 (always enqueued, exits at once when nothing overflowed): global-memory visited table
   HnswArgs b = a;
   b.qlist = a.overflow_list;
   b.nq_dev = a.overflow_count;
+  b.overflow_list = nullptr;
   // 8x the shared-memory table, never more than 2x the row count (a table that cannot fill up)
   b.hash_size = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)1 << 20, next_pow2(a.n_rows) * 2ull),
                                              std::max<uint64_t>(next_pow2(a.hash_size) * 8ull, 1024));
   b.hash_size = std::max<uint32_t>(b.hash_size, 1024u);
-  const int grid2 = std::min<int>(sms, (int)blocks_needed);
-  SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * HNSW_WARPS * b.hash_size));
-  const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true) * HNSW_WARPS;
-  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true>), smem2);
+  const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
+  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GATHER>), smem2);
+  int per_sm2 = 0;
+  SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hnsw_search_kernel<METRIC, true, GATHER>, warps * 32, smem2));
+  // the tables live in global memory (1-4 MB per warp at the largest size): bound their total
+  const uint64_t max_blocks2 = std::max<uint64_t>(1, ((uint64_t)512 << 20) / ((uint64_t)warps * b.hash_size * 4));
+  const int grid2 = (int)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms * std::max(per_sm2, 1), max_blocks2), blocks_needed);
+  SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * warps * b.hash_size));
   if (prof) prof->begin("hnsw_search_overflow");
-  hnsw_search_kernel<METRIC, true><<<grid2, HNSW_WARPS * 32, smem2, stream>>>(b);
+  hnsw_search_kernel<METRIC, true, GATHER><<<grid2, warps * 32, smem2, stream>>>(b);
   SCN_LAUNCHED();
   if (prof) prof->end();
   return SCN_OK;
@@ -475,6 +582,11 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.s0 = 2 * (uint32_t)s->m;
   a.su = (uint32_t)s->m;
   a.has_deleted = (s->live != s->rows) ? 1u : 0u;
+  const bool gather = s->opt_hnsw_gather != 0;
+  a.global_first = s->opt_hnsw_global ? 1u : 0u;
+  a.early_issue = s->opt_hnsw_early ? 1u : 0u;
+  a.max_per_sm = (uint32_t)std::max<int64_t>(0, s->opt_hnsw_per_sm);
+  a.stages = (a.pitch * 4 > GA_CHUNK) ? 2u : 1u;
   a.entry_row = s->entry_row;
   a.max_layer = s->max_layer;
   a.q = d_q;
@@ -486,19 +598,30 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.ef_pad = std::max(32u, next_pow2(ef));
   // visited table: ~2M*1.25 rows per expansion, ~ef expansions; keep it under 7/8 full
   a.hash_size = round_up(std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>((uint64_t)ef * (uint32_t)s->m * 5 / 2, 1u << 16)), 512);
+  if (s->opt_hnsw_hash > 0) a.hash_size = round_up((uint32_t)std::min<int64_t>(s->opt_hnsw_hash, 1 << 16), 512);
   a.out_ids = d_out_ids;
   a.out_dist = d_out_dist;
   a.out_counts = d_out_counts;
   SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
   a.stats = s->opt_profile ? s->d_counters : nullptr;
   // shrink the table until at least one block fits
-  while (hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false) * HNSW_WARPS > 200 * 1024 && a.hash_size > 1024)
+  while (!a.global_first &&
+         hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, gather ? a.stages : 0) * (gather ? 1 : HNSW_MAX_WARPS) > 200 * 1024 &&
+         a.hash_size > 1024)
     a.hash_size = round_up(a.hash_size / 2, 512);
   int32_t rc;
-  switch (s->metric) {
-    case M_L2: rc = launch_hnsw<M_L2>(a, sms, stream, scratch, prof); break;
-    case M_COS: rc = launch_hnsw<M_COS>(a, sms, stream, scratch, prof); break;
-    default: rc = launch_hnsw<M_IP>(a, sms, stream, scratch, prof); break;
+  if (gather) {
+    switch (s->metric) {
+      case M_L2: rc = launch_hnsw<M_L2, true>(a, sms, stream, scratch, prof); break;
+      case M_COS: rc = launch_hnsw<M_COS, true>(a, sms, stream, scratch, prof); break;
+      default: rc = launch_hnsw<M_IP, true>(a, sms, stream, scratch, prof); break;
+    }
+  } else {
+    switch (s->metric) {
+      case M_L2: rc = launch_hnsw<M_L2, false>(a, sms, stream, scratch, prof); break;
+      case M_COS: rc = launch_hnsw<M_COS, false>(a, sms, stream, scratch, prof); break;
+      default: rc = launch_hnsw<M_IP, false>(a, sms, stream, scratch, prof); break;
+    }
   }
   SCN_TRY(rc);
   return SCN_OK;

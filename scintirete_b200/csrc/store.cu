@@ -587,6 +587,16 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_min_batch = value;
   } else if (n == "overfetch") {
     s->opt_overfetch = value;
+  } else if (n == "hnsw_gather") {
+    s->opt_hnsw_gather = value;
+  } else if (n == "hnsw_global") {
+    s->opt_hnsw_global = value;
+  } else if (n == "hnsw_per_sm") {
+    s->opt_hnsw_per_sm = value;
+  } else if (n == "hnsw_early") {
+    s->opt_hnsw_early = value;
+  } else if (n == "hnsw_hash") {
+    s->opt_hnsw_hash = value;
   } else if (n == "tensor_hint") {
     s->opt_tensor_hint = value;
   } else if (n == "tensor_bn") {
