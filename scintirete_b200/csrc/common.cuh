@@ -287,41 +287,50 @@ __device__ __forceinline__ uint32_t cvta_smem(const void* p) { return (uint32_t)
 // per instruction: L1-tag-bound, 253 registers); one 1-D bulk copy (UBLKCP) per lane and row 5.9 ms —
 // exactly the copy engine's request rate (one request per ~46 cycles and SM: 39.9 M requests / 148
 // SMs); warp-wide cp.async: see profiles/.
-// `stage` holds 2 x 32 x GA_ROW bytes (one buffer suffices when a row is a single piece).
-constexpr uint32_t GA_CHUNK = 512;
-constexpr uint32_t GA_ROW = GA_CHUNK + 16;
+// CH = bytes of a row per stage (512, or 256: two rows per instruction), NBUF = stage buffers:
+//   <512, 2>  rows longer than 512 bytes: two stages in flight            (32 x 528 x 2 bytes)
+//   <512, 1>  rows of <= 512 bytes, one stage                             (32 x 528 bytes)
+//   <256, 1>  half the shared memory, stages strictly one after the other (32 x 272 bytes): the
+//             smallest footprint — for walks whose parallelism is bounded by shared memory
+__host__ __device__ constexpr uint32_t ga_row(uint32_t ch) { return ch + 16; }  // stage rows: conflict-free LDS.128
+__host__ __device__ constexpr uint32_t ga_stage_bytes(uint32_t ch, uint32_t nbuf) { return nbuf * 32 * ga_row(ch); }
 
-// stage `ch` of the rows of all lanes in `mask` -> buffer ch & 1, one commit group
+// stage `ch` of the rows of all lanes in `mask` -> buffer ch % NBUF, one commit group
+template <uint32_t CH, uint32_t NBUF>
 __device__ __forceinline__ void gather_issue(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask, uint32_t ch,
                                              unsigned char* stage, uint32_t lane) {
+  constexpr uint32_t LPR = CH / 16;   // lanes per row and instruction
+  constexpr uint32_t RPI = 32 / LPR;  // rows per instruction
   const uint32_t row_bytes = pitch * 4;  // multiple of 32
-  const uint32_t bytes = min(GA_CHUNK, row_bytes - ch * GA_CHUNK);
-  const bool mine = lane * 16 < bytes;
-  const uint32_t dst0 = cvta_smem(stage + (ch & 1) * 32 * GA_ROW + lane * 16);
-  const float* src0 = vec + (size_t)ch * (GA_CHUNK / 4) + lane * 4;
+  const uint32_t bytes = min(CH, row_bytes - ch * CH);
+  const uint32_t sub = lane / LPR, piece = lane % LPR;
+  const bool mine = piece * 16 < bytes;
+  const uint32_t dst0 = cvta_smem(stage + ((ch % NBUF) * 32 + sub) * ga_row(CH) + piece * 16);
+  const float* src0 = vec + (size_t)ch * (CH / 4) + piece * 4;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const uint32_t r = __shfl_sync(0xffffffffu, row, i);
-    if (((mask >> i) & 1u) && mine)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + i * GA_ROW), "l"(src0 + (size_t)r * pitch) : "memory");
+  for (uint32_t i = 0; i < 32; i += RPI) {
+    const uint32_t r = __shfl_sync(0xffffffffu, row, i + sub);
+    if (((mask >> (i + sub)) & 1u) && mine)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + i * ga_row(CH)), "l"(src0 + (size_t)r * pitch) : "memory");
   }
   cp_async_commit();
 }
-// the first one or two stages of a gather (what fits the buffers); gather_finish issues the rest
+// the first stage(s) of a gather (what fits the buffers); gather_finish issues the rest
+template <uint32_t CH, uint32_t NBUF>
 __device__ __forceinline__ void gather_begin(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask,
                                              unsigned char* stage, uint32_t lane) {
-  gather_issue(vec, pitch, row, mask, 0, stage, lane);
-  if (pitch * 4 > GA_CHUNK) gather_issue(vec, pitch, row, mask, 1, stage, lane);
+  gather_issue<CH, NBUF>(vec, pitch, row, mask, 0, stage, lane);
+  if (NBUF > 1 && pitch * 4 > CH) gather_issue<CH, NBUF>(vec, pitch, row, mask, 1, stage, lane);
 }
 // Completes a gather begun for a superset of the lanes in `mask` (lanes may have been dropped
 // since, e.g. rows found in the visited set while their copies were in flight: their data is
 // ignored, later stages are requested for the lanes of `mask` only). Returns +Inf on other lanes.
-template <int METRIC>
+template <int METRIC, uint32_t CH, uint32_t NBUF>
 __device__ __forceinline__ float gather_finish(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
                                                const float* sq, float qn, uint32_t row, uint32_t mask, unsigned char* stage,
                                                uint32_t lane) {
   const uint32_t row_bytes = pitch * 4;
-  const uint32_t n_chunks = (row_bytes + GA_CHUNK - 1) / GA_CHUNK;
+  const uint32_t n_chunks = (row_bytes + CH - 1) / CH;
   const bool valid = (mask >> lane) & 1u;
   if (!mask) {  // nobody left: drain what was begun
     cp_async_wait<0>();
@@ -331,16 +340,16 @@ __device__ __forceinline__ float gather_finish(const float* __restrict__ vec, co
   float acc = 0.0f;
   const float xn = (METRIC == M_COS && valid) ? __ldg(norm + row) : 0.0f;
   for (uint32_t ch = 0; ch < n_chunks; ++ch) {
-    if (ch + 1 < n_chunks) cp_async_wait<1>();  // stage ch + 1 may still be in flight
+    if (NBUF > 1 && ch + 1 < n_chunks) cp_async_wait<1>();  // stage ch + 1 may still be in flight
     else cp_async_wait<0>();
     __syncwarp();  // every lane's pieces of this stage have landed
-    const uint32_t n4 = min(GA_CHUNK, row_bytes - ch * GA_CHUNK) / 16;
+    const uint32_t n4 = min(CH, row_bytes - ch * CH) / 16;
     if (valid) {
-      const float4* x4 = reinterpret_cast<const float4*>(stage + ((ch & 1) * 32 + lane) * GA_ROW);
-      const float4* q4 = reinterpret_cast<const float4*>(sq) + ch * (GA_CHUNK / 16);
-      if (n4 == GA_CHUNK / 16) {
+      const float4* x4 = reinterpret_cast<const float4*>(stage + ((ch % NBUF) * 32 + lane) * ga_row(CH));
+      const float4* q4 = reinterpret_cast<const float4*>(sq) + ch * (CH / 16);
+      if (n4 == CH / 16) {
 #pragma unroll
-        for (uint32_t i = 0; i < GA_CHUNK / 16; ++i) {
+        for (uint32_t i = 0; i < CH / 16; ++i) {
           const float4 xa = x4[i], qa = q4[i];
           acc = acc_step<METRIC>(acc, qa.x, xa.x);
           acc = acc_step<METRIC>(acc, qa.y, xa.y);
@@ -358,17 +367,17 @@ __device__ __forceinline__ float gather_finish(const float* __restrict__ vec, co
       }
     }
     __syncwarp();  // this buffer is free again
-    if (ch + 2 < n_chunks) gather_issue(vec, pitch, row, mask, ch + 2, stage, lane);
+    if (ch + NBUF < n_chunks) gather_issue<CH, NBUF>(vec, pitch, row, mask, ch + NBUF, stage, lane);
   }
   return valid ? finish_distance<METRIC>(acc, qn, xn) : __int_as_float(0x7f800000);
 }
 
-template <int METRIC>
+template <int METRIC, uint32_t CH, uint32_t NBUF>
 __device__ __forceinline__ float gather_distance(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
                                                  const float* sq, float qn, uint32_t row, uint32_t mask, unsigned char* stage,
                                                  uint32_t lane) {
-  gather_begin(vec, pitch, row, mask, stage, lane);
-  return gather_finish<METRIC>(vec, norm, pitch, sq, qn, row, mask, stage, lane);
+  gather_begin<CH, NBUF>(vec, pitch, row, mask, stage, lane);
+  return gather_finish<METRIC, CH, NBUF>(vec, norm, pitch, sq, qn, row, mask, stage, lane);
 }
 
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

@@ -361,7 +361,7 @@ int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64
 // the first k distinct ones.
 
 __host__ __device__ inline size_t rerank_smem_bytes(uint32_t pitch, uint32_t ncand_pad) {
-  return (size_t)pitch * 4 + (size_t)ncand_pad * 8 + 2 * 32 * GA_ROW;
+  return (size_t)pitch * 4 + (size_t)ncand_pad * 8 + ga_stage_bytes(512, 2);
 }
 
 template <int METRIC>
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(32) rerank_kernel(const float* __restrict__ ve
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_q = reinterpret_cast<float*>(smem_raw);                                   // [pitch]
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q + pitch);                       // [ncand_pad]
-  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_keys + ncand_pad);     // [2][32][GA_ROW]
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_keys + ncand_pad);     // [2][32][528]
   const uint32_t lane = threadIdx.x;
   const uint32_t n_slots = nq_dev ? min(*nq_dev, nq) : nq;
   for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(32) rerank_kernel(const float* __restrict__ ve
       const uint32_t mask = __ballot_sync(0xffffffffu, valid);
       uint64_t key = KEY_NONE;
       if (mask) {
-        const float d = gather_distance<METRIC>(vec, norm, pitch, s_q, qnorm, row, mask, s_stage, lane);
+        const float d = gather_distance<METRIC, 512, 2>(vec, norm, pitch, s_q, qnorm, row, mask, s_stage, lane);
         if (valid) key = make_key(d, row + row_base);
       }
       s_keys[c] = key;

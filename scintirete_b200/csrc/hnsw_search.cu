@@ -32,6 +32,11 @@
 
 namespace scn {
 
+// GM, how the rows of a batch reach the lanes: 0 = LDG.256 into registers; else warp-wide cp.async
+// into shared memory (common.cuh): 1 = <512, 1>, 2 = <512, 2> (rows > 512 bytes), 3 = <256, 1>
+__host__ __device__ constexpr uint32_t gm_ch(int gm) { return gm == 3 ? 256u : 512u; }
+__host__ __device__ constexpr uint32_t gm_nbuf(int gm) { return gm == 2 ? 2u : 1u; }
+__host__ __device__ constexpr uint32_t gm_bytes(int gm) { return gm == 0 ? 0u : ga_stage_bytes(gm_ch(gm), gm_nbuf(gm)); }
 constexpr int HNSW_MAX_WARPS = 2;  // warps (= queries) per CTA: 2 for the register gather, 1 for the shared-memory gather
 constexpr uint32_t HASH_EMPTY = 0u;
 
@@ -49,7 +54,6 @@ struct HnswArgs {
   uint32_t has_deleted;    // 0: no row is soft-deleted, the bitmap need not be read
   uint32_t global_first;   // 1: the first pass keeps its visited tables in global memory too (L2-resident; more warps per SM)
   uint32_t early_issue;    // shared-memory gather: request the rows of a list before the visited test
-  uint32_t stages;         // shared-memory gather: stage buffers per warp (1 when a row is one 512-byte piece, else 2)
   uint32_t entry_row;
   int32_t max_layer;
   const float* q;
@@ -68,10 +72,10 @@ struct HnswArgs {
 };
 
 __host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t hash_size, bool global_hash,
-                                                  uint32_t stages) {
+                                                  uint32_t stage_bytes) {
   // wkey[2][ef_pad] u64 | snk[32] u64 | q[pitch] f32 | wrow[2][ef_pad] u32 | snr[32] u32 |
-  // stage[stages][32][GA_ROW] (shared-memory gather only) | hash
-  return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + (size_t)stages * 32 * GA_ROW +
+  // stage (shared-memory gather only) | hash
+  return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + stage_bytes +
          (global_hash ? 0 : (size_t)hash_size * 4);
 }
 
@@ -125,11 +129,10 @@ __device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups,
 // want == false only take part in the collectives. Returns true on a first visit.
 __device__ __forceinline__ bool visited_insert_warp(uint32_t* tab, uint32_t n_groups, uint32_t row, bool want, bool have_pre,
                                                     uint4 pre, uint32_t lane) {
+  // (An adjacency list never names a row twice: scn_graph_upload drops repeats, which the
+  // reference would skip as visited anyway. So the lanes of a batch hold distinct rows.)
   const uint32_t key = row + 1;
-  const uint32_t lt = (1u << lane) - 1u;
-  // the same row twice in one batch: the first lane inserts, the others see it as visited
-  const uint32_t same = __match_any_sync(0xffffffffu, key) & __ballot_sync(0xffffffffu, want);
-  bool pending = want && !(same & lt);
+  bool pending = want;
   bool fresh = false;
   uint32_t g = home_group(row, n_groups);
   for (uint32_t round = 0; round <= n_groups; ++round) {
@@ -140,10 +143,17 @@ __device__ __forceinline__ bool visited_insert_warp(uint32_t* tab, uint32_t n_gr
       if (v.x == key || v.y == key || v.z == key || v.w == key) pending = false;
       else e = (v.x == HASH_EMPTY) ? 0 : (v.y == HASH_EMPTY) ? 1 : (v.z == HASH_EMPTY) ? 2 : (v.w == HASH_EMPTY) ? 3 : 4;
     }
-    const bool ins = pending && e < 4;
-    const uint32_t peers = __match_any_sync(0xffffffffu, g) & __ballot_sync(0xffffffffu, ins);
+    // rank among the lower lanes that want a slot of the same group (31 shuffles: a third of the
+    // latency of MATCH.ANY on ~26 distinct values)
+    const uint32_t gi = (pending && e < 4) ? g : 0xFFFFFFFFu;
+    uint32_t rank = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 31; ++j) {
+      const uint32_t gj = __shfl_sync(0xffffffffu, gi, j);
+      rank += (j < lane && gj == g) ? 1u : 0u;
+    }
     if (pending) {
-      const uint32_t slot = (uint32_t)e + __popc(peers & lt);
+      const uint32_t slot = (uint32_t)e + rank;
       if (slot < 4) {
         asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(tab + g * 4 + slot), "r"(key) : "memory");
         pending = false;
@@ -157,14 +167,16 @@ __device__ __forceinline__ bool visited_insert_warp(uint32_t* tab, uint32_t n_gr
   return fresh;
 }
 
-template <int METRIC, bool USE_GLOBAL, bool GATHER>
+template <int METRIC, bool USE_GLOBAL, int GM>
 __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswArgs a) {
+  constexpr bool GATHER = GM != 0;
+  constexpr uint32_t GCH = gm_ch(GM), GNB = gm_nbuf(GM);
   extern __shared__ __align__(16) unsigned char smem_hnsw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t block_warps = blockDim.x >> 5;
   const uint32_t warp_global = blockIdx.x * block_warps + warp;
   const uint32_t warps_total = gridDim.x * block_warps;
-  unsigned char* base = smem_hnsw + hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, USE_GLOBAL, GATHER ? a.stages : 0) * warp;
+  unsigned char* base = smem_hnsw + hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, USE_GLOBAL, gm_bytes(GM)) * warp;
   uint64_t* wkey0 = reinterpret_cast<uint64_t*>(base);
   uint64_t* wkey1 = wkey0 + a.ef_pad;
   uint64_t* snk = wkey1 + a.ef_pad;                              // sorted new keys
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
   uint32_t* wrow1 = wrow0 + a.ef_pad;
   uint32_t* snr = wrow1 + a.ef_pad;                              // rows of the sorted new keys
   unsigned char* stage = reinterpret_cast<unsigned char*>(snr + 32);
-  uint32_t* smem_hash = reinterpret_cast<uint32_t*>(stage + (GATHER ? (size_t)a.stages * 32 * GA_ROW : 0));
+  uint32_t* smem_hash = reinterpret_cast<uint32_t*>(stage + gm_bytes(GM));
   uint32_t* hash = USE_GLOBAL ? (a.ghash + (size_t)warp_global * a.hash_size) : smem_hash;
   const uint32_t ef = a.ef;
   const uint32_t n_groups = a.hash_size >> 2;  // hash_size is a multiple of 4
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
             // fetched for nothing; bandwidth is not what bounds the walk.
             const uint32_t listed = __ballot_sync(0xffffffffu, ok);
             if (listed && a.early_issue) {
-              gather_begin(a.vec, a.pitch, nb, listed, stage, lane);
+              gather_begin<GCH, GNB>(a.vec, a.pitch, nb, listed, stage, lane);
               begun = true;
             }
           }
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
           }
           if (!ns) {  // nothing new in this chunk
             if (GATHER && begun) {  // drain the copies
-              gather_finish<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb, 0u, stage, lane);
+              gather_finish<METRIC, GCH, GNB>(a.vec, a.norm, a.pitch, sq, qn, nb, 0u, stage, lane);
               begun = false;
             }
             c0 += 32;
@@ -354,8 +366,8 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
         // per row and stage to the copy engine, rows land in shared memory)
         float d = INF;
         if (GATHER) {
-          if (!begun) gather_begin(a.vec, a.pitch, nb, mask, stage, lane);
-          d = gather_finish<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
+          if (!begun) gather_begin<GCH, GNB>(a.vec, a.pitch, nb, mask, stage, lane);
+          d = gather_finish<METRIC, GCH, GNB>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
         }
         else if (ok) d = row_distance<METRIC>(a.vec, a.norm, a.pitch, sq, qn, nb);
 
@@ -503,37 +515,37 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
   }
 }
 
-template <int METRIC, bool GATHER>
+template <int METRIC, int GM>
 static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
   // pass 1: shared-memory visited table (or, global_first, a table of the same size in global memory)
-  const int warps = GATHER ? 1 : HNSW_MAX_WARPS;
-  const uint32_t stages = GATHER ? a.stages : 0;
+  const int warps = GM ? 1 : HNSW_MAX_WARPS;
+  const uint32_t stages = gm_bytes(GM);
   const uint32_t blocks_needed = (a.nq + warps - 1) / warps;
   SCN_TRY(scratch.alloc(&a.overflow_list, (size_t)a.nq));
   SCN_TRY(scratch.alloc(&a.overflow_count, 1));
   SCN_CUDA(cudaMemsetAsync(a.overflow_count, 0, sizeof(uint32_t), stream));
   if (!a.global_first) {
     const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, stages) * warps;
-    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, false, GATHER>), smem);
+    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, false, GM>), smem);
     int per_sm = 0;
-    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false, GATHER>, warps * 32, smem));
+    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, false, GM>, warps * 32, smem));
     if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
     const int grid = (int)std::min<uint32_t>(blocks_needed, (uint32_t)(sms * per_sm));
     if (prof) prof->begin("hnsw_search");
-    hnsw_search_kernel<METRIC, false, GATHER><<<grid, warps * 32, smem, stream>>>(a);
+    hnsw_search_kernel<METRIC, false, GM><<<grid, warps * 32, smem, stream>>>(a);
     SCN_LAUNCHED();
     if (prof) prof->end();
   } else {
     const size_t smem = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
-    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GATHER>), smem);
+    SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GM>), smem);
     int per_sm = 0;
-    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, true, GATHER>, warps * 32, smem));
+    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_search_kernel<METRIC, true, GM>, warps * 32, smem));
     if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", a.ef, a.dim);
     if (a.max_per_sm > 0) per_sm = std::min<int>(per_sm, (int)a.max_per_sm);
     const int grid = (int)std::min<uint32_t>(blocks_needed, (uint32_t)(sms * per_sm));
     SCN_TRY(scratch.alloc(&a.ghash, (size_t)grid * warps * a.hash_size));
     if (prof) prof->begin("hnsw_search");
-    hnsw_search_kernel<METRIC, true, GATHER><<<grid, warps * 32, smem, stream>>>(a);
+    hnsw_search_kernel<METRIC, true, GM><<<grid, warps * 32, smem, stream>>>(a);
     SCN_LAUNCHED();
     if (prof) prof->end();
   }
@@ -547,15 +559,15 @@ static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& s
                                              std::max<uint64_t>(next_pow2(a.hash_size) * 8ull, 1024));
   b.hash_size = std::max<uint32_t>(b.hash_size, 1024u);
   const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
-  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GATHER>), smem2);
+  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GM>), smem2);
   int per_sm2 = 0;
-  SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hnsw_search_kernel<METRIC, true, GATHER>, warps * 32, smem2));
+  SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hnsw_search_kernel<METRIC, true, GM>, warps * 32, smem2));
   // the tables live in global memory (1-4 MB per warp at the largest size): bound their total
   const uint64_t max_blocks2 = std::max<uint64_t>(1, ((uint64_t)512 << 20) / ((uint64_t)warps * b.hash_size * 4));
   const int grid2 = (int)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms * std::max(per_sm2, 1), max_blocks2), blocks_needed);
   SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * warps * b.hash_size));
   if (prof) prof->begin("hnsw_search_overflow");
-  hnsw_search_kernel<METRIC, true, GATHER><<<grid2, warps * 32, smem2, stream>>>(b);
+  hnsw_search_kernel<METRIC, true, GM><<<grid2, warps * 32, smem2, stream>>>(b);
   SCN_LAUNCHED();
   if (prof) prof->end();
   return SCN_OK;
@@ -582,11 +594,14 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.s0 = 2 * (uint32_t)s->m;
   a.su = (uint32_t)s->m;
   a.has_deleted = (s->live != s->rows) ? 1u : 0u;
-  const bool gather = s->opt_hnsw_gather != 0;
+  // gather mode (see gm_ch): rows longer than 512 bytes take two 512-byte stages
+  int gm = (int)s->opt_hnsw_gather;
+  if (gm < 0 || gm > 3) gm = 1;
+  if (gm != 0 && a.pitch * 4 > 512) gm = 2;
+  if (gm == 2 && a.pitch * 4 <= 512) gm = 1;
   a.global_first = s->opt_hnsw_global ? 1u : 0u;
   a.early_issue = s->opt_hnsw_early ? 1u : 0u;
   a.max_per_sm = (uint32_t)std::max<int64_t>(0, s->opt_hnsw_per_sm);
-  a.stages = (a.pitch * 4 > GA_CHUNK) ? 2u : 1u;
   a.entry_row = s->entry_row;
   a.max_layer = s->max_layer;
   a.q = d_q;
@@ -598,6 +613,8 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.ef_pad = std::max(32u, next_pow2(ef));
   // visited table: ~2M*1.25 rows per expansion, ~ef expansions; keep it under 7/8 full
   a.hash_size = round_up(std::max<uint32_t>(1024u, (uint32_t)std::min<uint64_t>((uint64_t)ef * (uint32_t)s->m * 5 / 2, 1u << 16)), 512);
+  // global tables cost no shared memory: 4x the entries keep the groups sparse (fewer second probe rounds)
+  if (a.global_first) a.hash_size = (uint32_t)std::min<uint64_t>((uint64_t)next_pow2(a.hash_size) * 2, 1u << 16);
   if (s->opt_hnsw_hash > 0) a.hash_size = round_up((uint32_t)std::min<int64_t>(s->opt_hnsw_hash, 1 << 16), 512);
   a.out_ids = d_out_ids;
   a.out_dist = d_out_dist;
@@ -605,24 +622,23 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
   a.stats = s->opt_profile ? s->d_counters : nullptr;
   // shrink the table until at least one block fits
-  while (!a.global_first &&
-         hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, gather ? a.stages : 0) * (gather ? 1 : HNSW_MAX_WARPS) > 200 * 1024 &&
+  while (!a.global_first && hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, gm_bytes(gm)) * (gm ? 1 : HNSW_MAX_WARPS) > 200 * 1024 &&
          a.hash_size > 1024)
     a.hash_size = round_up(a.hash_size / 2, 512);
   int32_t rc;
-  if (gather) {
-    switch (s->metric) {
-      case M_L2: rc = launch_hnsw<M_L2, true>(a, sms, stream, scratch, prof); break;
-      case M_COS: rc = launch_hnsw<M_COS, true>(a, sms, stream, scratch, prof); break;
-      default: rc = launch_hnsw<M_IP, true>(a, sms, stream, scratch, prof); break;
-    }
-  } else {
-    switch (s->metric) {
-      case M_L2: rc = launch_hnsw<M_L2, false>(a, sms, stream, scratch, prof); break;
-      case M_COS: rc = launch_hnsw<M_COS, false>(a, sms, stream, scratch, prof); break;
-      default: rc = launch_hnsw<M_IP, false>(a, sms, stream, scratch, prof); break;
-    }
+#define HN(MT)                                                                  \
+  switch (gm) {                                                                 \
+    case 0: rc = launch_hnsw<MT, 0>(a, sms, stream, scratch, prof); break;      \
+    case 1: rc = launch_hnsw<MT, 1>(a, sms, stream, scratch, prof); break;      \
+    case 2: rc = launch_hnsw<MT, 2>(a, sms, stream, scratch, prof); break;      \
+    default: rc = launch_hnsw<MT, 3>(a, sms, stream, scratch, prof); break;     \
   }
+  switch (s->metric) {
+    case M_L2: HN(M_L2); break;
+    case M_COS: HN(M_COS); break;
+    default: HN(M_IP); break;
+  }
+#undef HN
   SCN_TRY(rc);
   return SCN_OK;
 }

@@ -543,15 +543,21 @@ int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t en
         return fail(SCN_ERR_INVALID_PARAMETERS, "node %llu layer %d has %u neighbours (max %u)",
                     (unsigned long long)node_ids[i], l, c, cap_l);
       uint32_t* dst = (l == 0) ? &adj0[(size_t)r * s0] : &adj_up[((size_t)up_off[r] + (l - 1)) * su];
+      // A neighbour named twice is kept once, at its first position: searchLayer skips the second
+      // occurrence as visited (hnsw.go:523-525; as deleted, 527-530, if the first one was), so the
+      // walk is the same, and the kernels may rely on a list holding distinct rows.
+      uint32_t kept = 0;
       for (uint32_t e = 0; e < c; ++e) {
         uint32_t nr;
         if (!s->lookup(edges[ei + e], &nr))
           return fail(SCN_ERR_INDEX_BUILD_FAILED, "neighbour %llu of node %llu is not in the store",
                       (unsigned long long)edges[ei + e], (unsigned long long)node_ids[i]);
-        dst[e] = nr;
+        bool seen = false;
+        for (uint32_t f = 0; f < kept && !seen; ++f) seen = dst[f] == nr;
+        if (!seen) dst[kept++] = nr;
       }
       ei += c;
-      total_edges += c;
+      total_edges += kept;
     }
   }
   uint32_t entry_row = ROW_NONE;
