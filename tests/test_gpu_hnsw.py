@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from scintirete_b200 import DistanceMetric, GPUHNSWIndex, HNSWParams, ScintireteError, SearchParams
+from scintirete_b200 import DistanceMetric, GPUHNSWIndex, GraphState, HNSWParams, ScintireteError, SearchParams
 from util import gaussian, recall, to_graph_state
 
 pytestmark = pytest.mark.gpu
@@ -132,3 +132,47 @@ def test_walk_is_identical_to_the_reference_walk(metric, d):
     assert np.array_equal(ids, o_ids)
     assert np.array_equal(dist, o_dist)
     assert counters[1] == o_stats[1], (counters, o_stats)   # expansions, all layers
+
+
+@pytest.mark.parametrize("d", [128, 200, 768])
+@pytest.mark.parametrize("gather,global_tables", [(0, 0), (0, 1), (1, 0), (1, 1), (3, 0), (3, 1)])
+def test_walk_is_identical_in_every_gather_and_table_mode(d, gather, global_tables):
+    # the kernel's switches (rows through registers / 512-byte / 256-byte shared-memory stages;
+    # visited tables in shared or global memory) change how a walk is executed, never the walk:
+    # ids, distance bits and expansion counts stay the oracle's. d = 200 and 768 take the ragged
+    # last stage and the two-buffer path (rows longer than 512 bytes).
+    n, nq, k, ef = 3000, 100, 10, 48
+    db, h, g = _pair(DistanceMetric.L2, n, d, efc=60)
+    q = gaussian(nq, d, 7)
+    o_ids, o_dist, o_cnt, o_stats = h.search_batch(q, k, ef, nthreads=8)
+    g.store.set_option("hnsw_gather", gather)
+    g.store.set_option("hnsw_global", global_tables)
+    g.store.set_option("profile", 1)
+    ids, dist, cnt = g.search_batch(q, SearchParams(top_k=k, ef_search=ef))
+    counters = g.store.last_counters()
+    assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist)
+    assert counters[1] == o_stats[1], (counters, o_stats)
+
+
+def test_repeated_neighbours_are_dropped_at_upload_like_visited_rows():
+    # a list that names a neighbour twice walks exactly like the list without the repeat
+    # (hnsw.go:523-525 skips the second occurrence as visited)
+    n, d = 400, 16
+    db, h, g = _pair(DistanceMetric.L2, n, d, M=8, efc=40)
+    st = h.export_graph_state()
+    edges, counts = [], []
+    pos = 0
+    for c in st.edge_counts:
+        lst = list(st.edges[pos:pos + c])
+        pos += c
+        if 0 < c < 8:            # room for one repeat below the per-layer cap
+            lst.append(lst[0])
+        edges.extend(lst)
+        counts.append(len(lst))
+    g2 = GPUHNSWIndex(HNSWParams(m=8, ef_search=32), DistanceMetric.L2, d)
+    g2.import_graph_state(GraphState(st.ids, st.list_counts, np.asarray(counts, np.uint32), np.asarray(edges, np.uint64),
+                                     st.entrypoint, st.max_layer, st.size, st.deleted, st.vectors, m=8))
+    q = gaussian(40, d, 5)
+    a = g.search_batch(q, SearchParams(top_k=5, ef_search=32))
+    b = g2.search_batch(q, SearchParams(top_k=5, ef_search=32))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
