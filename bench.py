@@ -410,7 +410,7 @@ def run_ours(args, wl):
                 flops = 2.0 * nq * n_local * dim
                 ach = flops / (avg_ms * 1e-3) / 1e12
                 # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-                traffic = 10.39e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
+                traffic = 2.384e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
                 roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_sustained"], "traffic": traffic,
                         "traffic_source": "profiles/r01_ncu_tensor_filter_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
@@ -427,9 +427,15 @@ def run_ours(args, wl):
                 evals, hops = counters[0], counters[1]
                 byts = evals * dim * 4.0 + hops * 32 * 4.0
                 ach = byts / (avg_ms * 1e-3) / 1e9
+                # DRAM bytes per launch from the committed ncu --set full capture of this exact workload: BELOW the
+                # algorithmic bytes, because the walks of a batch share hub rows and L2 serves them
+                traffic = 8.726e9 if (rows, dim, nq, world, args.ef) == (1_000_000, 128, 10_000, 1, 128) else None
                 roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"], "launch_ms": avg_ms,
-                        "share_of_step": share, "note": f"{evals / nq:.0f} distance evals, {hops / nq:.0f} expansions per query (counted on device)"}
+                        "frac": ach / pk["hbm"], "traffic": traffic,
+                        "traffic_source": "profiles/r01_ncu_hnsw_search_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
+                        "algorithmic_bytes": byts, "peak_source": pk["source"], "launch_ms": avg_ms,
+                        "share_of_step": share, "note": f"{evals / nq:.0f} distance evals, {hops / nq:.0f} expansions per query (counted on device); "
+                                                        "algorithmic bytes = evals*dim*4 + expansions*2M*4"}
         # CPU baseline on a bounded sample (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
