@@ -102,6 +102,38 @@ __device__ __forceinline__ float acc_step(float acc, float q, float x) {
   }
 }
 
+// Four steps at once: the element-wise part (difference, product) on the packed fp32x2 pipe
+// (FADD2 / FMUL2: two IEEE round-to-nearest results per instruction, bit-identical to the scalar
+// ops), the four additions into the accumulator one after the other in source order.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+template <int METRIC>
+__device__ __forceinline__ float acc_step4(float acc, const float4& q, const float4& x) {
+  unsigned long long p01, p23;
+  const unsigned long long q01 = pack_f32x2(q.x, q.y), q23 = pack_f32x2(q.z, q.w);
+  const unsigned long long x01 = pack_f32x2(x.x, x.y), x23 = pack_f32x2(x.z, x.w);
+  if (METRIC == M_L2) {
+    unsigned long long d01, d23;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(q01), "l"(x01));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(q23), "l"(x23));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(p01) : "l"(d01));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(p23) : "l"(d23));
+  } else {
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p01) : "l"(q01), "l"(x01));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p23) : "l"(q23), "l"(x23));
+  }
+  float t0, t1, t2, t3;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(p01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t2), "=f"(t3) : "l"(p23));
+  acc = __fadd_rn(acc, t0);
+  acc = __fadd_rn(acc, t1);
+  acc = __fadd_rn(acc, t2);
+  return __fadd_rn(acc, t3);
+}
+
 // acc = the sequential sum; qnorm / xnorm = sqrt of the sequential sums of squares (cosine only).
 template <int METRIC>
 __device__ __forceinline__ float finish_distance(float acc, float qnorm, float xnorm) {
@@ -126,10 +158,7 @@ __device__ __forceinline__ float exact_acc_thread(const float* __restrict__ q, c
   for (uint32_t i = 0; i < pitch4; ++i) {
     float4 a = q4[i];
     float4 b = __ldg(x4 + i);
-    acc = acc_step<METRIC>(acc, a.x, b.x);
-    acc = acc_step<METRIC>(acc, a.y, b.y);
-    acc = acc_step<METRIC>(acc, a.z, b.z);
-    acc = acc_step<METRIC>(acc, a.w, b.w);
+    acc = acc_step4<METRIC>(acc, a, b);
   }
   return acc;
 }
@@ -177,10 +206,7 @@ __device__ __forceinline__ float acc_chunk(float acc, const float4 (&b)[DCH], co
   }
 #pragma unroll
   for (int i = 0; i < DCH; ++i) {
-    acc = acc_step<METRIC>(acc, qa[i].x, b[i].x);
-    acc = acc_step<METRIC>(acc, qa[i].y, b[i].y);
-    acc = acc_step<METRIC>(acc, qa[i].z, b[i].z);
-    acc = acc_step<METRIC>(acc, qa[i].w, b[i].w);
+    acc = acc_step4<METRIC>(acc, qa[i], b[i]);
   }
   return acc;
 }
@@ -279,9 +305,9 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ uint32_t cvta_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- warp gather: the reference's Distance(query, row) for up to 32 rows, one per lane ------------
-// The rows of a batch are copied into shared memory with warp-wide cp.async: ONE instruction moves
-// 512 contiguous bytes of ONE row (16 bytes per lane), so DRAM sees whole bursts and L1 spends four
-// tag cycles per 512 bytes. Each lane then walks its own row (stage rows GA_ROW bytes apart:
+// The rows of a batch are copied into shared memory with warp-wide cp.async: one instruction moves
+// one whole 128-byte line of each of four rows (16 bytes per lane), so DRAM sees whole lines and L1
+// spends four tag cycles per instruction instead of 32. Each lane then walks its own row (stage rows GA_ROW bytes apart:
 // conflict-free LDS.128) in the reference's sequential fp32 order.
 // History (1 M x 128, ef = 128, 10 k queries): lane-per-row LDG.256 into registers 9.1 ms (32 lines
 // per instruction: L1-tag-bound, 253 registers); one 1-D bulk copy (UBLKCP) per lane and row 5.9 ms —
@@ -295,23 +321,49 @@ __device__ __forceinline__ uint32_t cvta_smem(const void* p) { return (uint32_t)
 __host__ __device__ constexpr uint32_t ga_row(uint32_t ch) { return ch + 16; }  // stage rows: conflict-free LDS.128
 __host__ __device__ constexpr uint32_t ga_stage_bytes(uint32_t ch, uint32_t nbuf) { return nbuf * 32 * ga_row(ch); }
 
-// stage `ch` of the rows of all lanes in `mask` -> buffer ch % NBUF, one commit group
+// stage `ch` of the rows of all lanes in `mask` -> buffer ch % NBUF, one commit group.
+// A quarter-warp copies one 128-byte line of one row per instruction (four rows per instruction,
+// the lines of a row by consecutive instructions with immediate offsets), so one shuffle and one
+// 64-bit address feed CH/128 copies.
 template <uint32_t CH, uint32_t NBUF>
 __device__ __forceinline__ void gather_issue(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask, uint32_t ch,
                                              unsigned char* stage, uint32_t lane) {
-  constexpr uint32_t LPR = CH / 16;   // lanes per row and instruction
-  constexpr uint32_t RPI = 32 / LPR;  // rows per instruction
   const uint32_t row_bytes = pitch * 4;  // multiple of 32
   const uint32_t bytes = min(CH, row_bytes - ch * CH);
-  const uint32_t sub = lane / LPR, piece = lane % LPR;
-  const bool mine = piece * 16 < bytes;
+  const uint32_t sub = lane >> 3, piece = lane & 7;
   const uint32_t dst0 = cvta_smem(stage + ((ch % NBUF) * 32 + sub) * ga_row(CH) + piece * 16);
-  const float* src0 = vec + (size_t)ch * (CH / 4) + piece * 4;
+  const unsigned char* src0 = reinterpret_cast<const unsigned char*>(vec) + (size_t)ch * CH + piece * 16;
+  // the row index doubles as the predicate: lanes outside `mask` hand out 0xFFFFFFFF
+  const uint32_t rowv = ((mask >> lane) & 1u) ? row : 0xFFFFFFFFu;
+  if (bytes == CH) {  // full stage: straight-line, predicated copies (no branch per row)
 #pragma unroll
-  for (uint32_t i = 0; i < 32; i += RPI) {
-    const uint32_t r = __shfl_sync(0xffffffffu, row, i + sub);
-    if (((mask >> (i + sub)) & 1u) && mine)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + i * ga_row(CH)), "l"(src0 + (size_t)r * pitch) : "memory");
+    for (uint32_t i = 0; i < 32; i += 4) {
+      const uint32_t r = __shfl_sync(0xffffffffu, rowv, i + sub);
+      const unsigned char* src = src0 + (size_t)r * row_bytes;  // not dereferenced when r is the marker
+      if (CH == 256)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0xffffffff;\n\t"
+                     "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+                     "@p cp.async.cg.shared.global [%0+128], [%1+128], 16;\n\t}" ::"r"(dst0 + i * ga_row(CH)), "l"(src), "r"(r) : "memory");
+      else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0xffffffff;\n\t"
+                     "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+                     "@p cp.async.cg.shared.global [%0+128], [%1+128], 16;\n\t"
+                     "@p cp.async.cg.shared.global [%0+256], [%1+256], 16;\n\t"
+                     "@p cp.async.cg.shared.global [%0+384], [%1+384], 16;\n\t}" ::"r"(dst0 + i * ga_row(CH)), "l"(src), "r"(r) : "memory");
+    }
+  } else {  // ragged last stage
+#pragma unroll
+    for (uint32_t i = 0; i < 32; i += 4) {
+      const uint32_t r = __shfl_sync(0xffffffffu, rowv, i + sub);
+      if (r != 0xFFFFFFFFu) {
+        const unsigned char* src = src0 + (size_t)r * row_bytes;
+#pragma unroll
+        for (uint32_t j = 0; j < CH / 128; ++j) {
+          if (piece * 16 + j * 128 < bytes)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + i * ga_row(CH) + j * 128), "l"(src + j * 128) : "memory");
+        }
+      }
+    }
   }
   cp_async_commit();
 }
@@ -351,18 +403,12 @@ __device__ __forceinline__ float gather_finish(const float* __restrict__ vec, co
 #pragma unroll
         for (uint32_t i = 0; i < CH / 16; ++i) {
           const float4 xa = x4[i], qa = q4[i];
-          acc = acc_step<METRIC>(acc, qa.x, xa.x);
-          acc = acc_step<METRIC>(acc, qa.y, xa.y);
-          acc = acc_step<METRIC>(acc, qa.z, xa.z);
-          acc = acc_step<METRIC>(acc, qa.w, xa.w);
+          acc = acc_step4<METRIC>(acc, qa, xa);
         }
       } else {
         for (uint32_t i = 0; i < n4; ++i) {
           const float4 xa = x4[i], qa = q4[i];
-          acc = acc_step<METRIC>(acc, qa.x, xa.x);
-          acc = acc_step<METRIC>(acc, qa.y, xa.y);
-          acc = acc_step<METRIC>(acc, qa.z, xa.z);
-          acc = acc_step<METRIC>(acc, qa.w, xa.w);
+          acc = acc_step4<METRIC>(acc, qa, xa);
         }
       }
     }

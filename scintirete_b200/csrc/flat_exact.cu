@@ -163,10 +163,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi) {
           float4 qv = *reinterpret_cast<const float4*>(s_q + (size_t)qi * p.dim_pad + chunk * SCAN_KC + j * 4);
-          acc[qi] = acc_step<METRIC>(acc[qi], qv.x, x.x);
-          acc[qi] = acc_step<METRIC>(acc[qi], qv.y, x.y);
-          acc[qi] = acc_step<METRIC>(acc[qi], qv.z, x.z);
-          acc[qi] = acc_step<METRIC>(acc[qi], qv.w, x.w);
+          acc[qi] = acc_step4<METRIC>(acc[qi], qv, x);
         }
       }
       if (chunk == n_chunks - 1) {
