@@ -153,9 +153,21 @@ struct FilterCfg {
   static constexpr int KSTEP = (BN == 64) ? 128 : 64;              // K elements per stage
   static constexpr int B_BYTES = BN * KSTEP * 2;                    // 16 KB either way
   static constexpr int STAGE_BYTES = (ASM ? TF_BM * TF_BK * 2 : 0) + B_BYTES;
-  static constexpr int STAGES = ASM ? (KP > 16 ? 5 : 6) : 10;
+  static constexpr int STAGES = ASM ? (KP > 16 ? 5 : 6) : ((KP > 16 && EW == 2) ? 9 : 10);  // what fits 227 KB next to the lists
   static_assert(!ASM || BN == 128, "the streamed-A variant uses 128-row tiles");
 };
+
+// packed fp32x2 FMA: {d0, d1} = c * {a0, a1} + {b0, b1} (one FFMA2; each half an IEEE fma)
+__device__ __forceinline__ void fma2(unsigned long long c2, float a0, float a1, float b0, float b1, float& d0, float& d1) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(c2), "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(r));
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 __global__ void __launch_bounds__(64 + 128 * EW, 1)
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   constexpr int KSTEP = Cfg::KSTEP;
   constexpr int TF_B_OFF = ASM ? (TF_BM * TF_BK * 2) : 0;  // B block within a stage (A block first when streamed)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve-up: [B stages][cand_row 128*EW*KP][queue 2*16*128*EW][aux 2*BN][barriers][tmem ptr]
+  // carve-up: [B stages][cand_row 128*EW*KP][queue 2*16*128*EW][aux 8*BN][barriers][tmem ptr]
   // 1024-byte alignment for the 128B-swizzled tiles; plain pointer arithmetic on the __shared__
   // array keeps the shared address space visible to the compiler (LDS/STS, not generic LD/ST)
   unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   float* s_qs = reinterpret_cast<float*>(s_crow + ET * KP);        // [16][ET] queued scores
   uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * ET);    // [16][ET] queued columns
   float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 2 * TF_BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 8 * TF_BN);  // 4*EW warps x 2 buffers x BN/EW columns
   uint64_t* full = bars;                     // [STAGES]  TMA -> MMA
   uint64_t* empty = full + TF_STAGES;        // [STAGES]  MMA -> TMA
   uint64_t* acc_full = empty + TF_STAGES;    // [2]       MMA -> epilogue
@@ -299,6 +311,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     float* my_qs = s_qs + slice * 128 + qrow;
     uint32_t* my_qc = s_qc + slice * 128 + qrow;
     uint32_t acc_it = 0;
+    const unsigned long long coef2 = pack_f32x2(a.coef, a.coef);
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / a.n_qblocks;
       const uint32_t qblk = item - chunk * a.n_qblocks;
@@ -340,23 +353,34 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       float theta = hint;  // min(hint, max of sc[]): the threshold every admitted row must beat
       int imax = 0;        // a slot holding theta
       // additive per-column term for the first tile, fetched one tile ahead from here on
-      float aux_next = INF;
-      if (et < TF_BN) {
-        uint32_t c = t0 * TF_BN + et;
-        if (t0 < t1 && c < a.n_rows) aux_next = __ldg(a.aux + c);
-      }
+      // Each warp stages the term of its own CW columns (lanes 0..CW/4-1, one float4 each) in a
+      // private double buffer: no block barrier per tile, so the epilogue warps are coupled only
+      // through the accumulator barriers and one warp's insertions no longer stall the other seven.
+      float* my_aux = s_aux + (warp - 2) * 2 * CW;
+      auto load_aux = [&](uint32_t t) -> float4 {
+        float4 r = make_float4(INF, INF, INF, INF);
+        if (lane < CW / 4 && t < t1) {
+          const uint32_t c = t * TF_BN + slice * CW + lane * 4;
+          if (c + 3 < a.n_rows) {
+            r = __ldg(reinterpret_cast<const float4*>(a.aux + c));
+          } else {
+            if (c + 0 < a.n_rows) r.x = __ldg(a.aux + c + 0);
+            if (c + 1 < a.n_rows) r.y = __ldg(a.aux + c + 1);
+            if (c + 2 < a.n_rows) r.z = __ldg(a.aux + c + 2);
+          }
+        }
+        return r;
+      };
+      float4 aux_next = load_aux(t0);
       for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
         const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
         const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
         const uint32_t col0 = t * TF_BN;
-        float* aux_t = s_aux + (acc_it & 1) * TF_BN;
+        float* aux_t = my_aux + (acc_it & 1) * CW;
         // per-column additive term (||x~||^2, 0, or +Inf for deleted / out-of-range rows)
-        if (et < TF_BN) {
-          aux_t[et] = aux_next;
-          uint32_t c = col0 + TF_BN + et;
-          aux_next = (t + 1 < t1 && c < a.n_rows) ? __ldg(a.aux + c) : INF;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+        if (lane < CW / 4) reinterpret_cast<float4*>(aux_t)[lane] = aux_next;
+        aux_next = load_aux(t + 1);
+        __syncwarp();
         mbar_wait(acc_full + buf, use & 1);
         tc_fence_after();
         float v[CW];
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         if (lane == 0) mbar_arrive(acc_empty + buf);
         // Gate four columns at a time (min of 4 against theta); survivors are queued in shared
         // memory and inserted by one loop per 16-column segment, so the unrolled code stays small.
-        const float4* aux4 = reinterpret_cast<const float4*>(aux_t + slice * CW);
+        const float4* aux4 = reinterpret_cast<const float4*>(aux_t);
         const uint32_t colw = col0 + slice * CW;  // first column of this warp's slice
         float4 ax[4];
 #pragma unroll
@@ -385,17 +409,17 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             const int j = seg * 16 + g4 * 4;
-            const float s0 = fmaf(a.coef, v[j + 0], ax[g4].x);
-            const float s1 = fmaf(a.coef, v[j + 1], ax[g4].y);
-            const float s2 = fmaf(a.coef, v[j + 2], ax[g4].z);
-            const float s3 = fmaf(a.coef, v[j + 3], ax[g4].w);
+            // two packed FMAs (FFMA2) for the four scores, one three-input min (FMNMX3) for the gate
+            float s0, s1, s2, s3;
+            fma2(coef2, v[j + 0], v[j + 1], ax[g4].x, ax[g4].y, s0, s1);
+            fma2(coef2, v[j + 2], v[j + 3], ax[g4].z, ax[g4].w, s2, s3);
             if (DBG) {
               v[j + 0] = s0;
               v[j + 1] = s1;
               v[j + 2] = s2;
               v[j + 3] = s3;
             }
-            if (fminf(fminf(s0, s1), fminf(s2, s3)) < theta) {
+            if (fminf(min3(s0, s1, s2), s3) < theta) {
               if (s0 < theta) { my_qs[cnt * ET] = s0; my_qc[cnt * ET] = colw + j + 0; ++cnt; }
               if (s1 < theta) { my_qs[cnt * ET] = s1; my_qc[cnt * ET] = colw + j + 1; ++cnt; }
               if (s2 < theta) { my_qs[cnt * ET] = s2; my_qc[cnt * ET] = colw + j + 2; ++cnt; }
@@ -659,7 +683,7 @@ template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
-                (size_t)2 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
+                (size_t)8 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
   SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>), smem);
   tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
   SCN_LAUNCHED();
