@@ -405,53 +405,66 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 #pragma unroll
             for (int i = 0; i < 4; ++i) axn[i] = aux4[(seg + 1) * 4 + i];
           }
-          uint32_t cnt = 0;
+          // All 16 scores of the segment first (8 FFMA2), then the minimum of each group of four
+          // and of the segment (FMNMX3): straight-line code with ONE branch per segment, taken only
+          // when some column beats the threshold (per warp about once per tile in steady state).
+          float sg[16], mg[4];
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             const int j = seg * 16 + g4 * 4;
-            // two packed FMAs (FFMA2) for the four scores, one three-input min (FMNMX3) for the gate
-            float s0, s1, s2, s3;
-            fma2(coef2, v[j + 0], v[j + 1], ax[g4].x, ax[g4].y, s0, s1);
-            fma2(coef2, v[j + 2], v[j + 3], ax[g4].z, ax[g4].w, s2, s3);
+            fma2(coef2, v[j + 0], v[j + 1], ax[g4].x, ax[g4].y, sg[g4 * 4 + 0], sg[g4 * 4 + 1]);
+            fma2(coef2, v[j + 2], v[j + 3], ax[g4].z, ax[g4].w, sg[g4 * 4 + 2], sg[g4 * 4 + 3]);
             if (DBG) {
-              v[j + 0] = s0;
-              v[j + 1] = s1;
-              v[j + 2] = s2;
-              v[j + 3] = s3;
+              v[j + 0] = sg[g4 * 4 + 0];
+              v[j + 1] = sg[g4 * 4 + 1];
+              v[j + 2] = sg[g4 * 4 + 2];
+              v[j + 3] = sg[g4 * 4 + 3];
             }
-            if (fminf(min3(s0, s1, s2), s3) < theta) {
-              if (s0 < theta) { my_qs[cnt * ET] = s0; my_qc[cnt * ET] = colw + j + 0; ++cnt; }
-              if (s1 < theta) { my_qs[cnt * ET] = s1; my_qc[cnt * ET] = colw + j + 1; ++cnt; }
-              if (s2 < theta) { my_qs[cnt * ET] = s2; my_qc[cnt * ET] = colw + j + 2; ++cnt; }
-              if (s3 < theta) { my_qs[cnt * ET] = s3; my_qc[cnt * ET] = colw + j + 3; ++cnt; }
-            }
+            mg[g4] = fminf(min3(sg[g4 * 4 + 0], sg[g4 * 4 + 1], sg[g4 * 4 + 2]), sg[g4 * 4 + 3]);
           }
-#pragma unroll 1
-          for (uint32_t i = 0; i < cnt; ++i) {
-            const float s = my_qs[i * ET];
-            if (s < theta) {
-              // replace the current worst, then find the new worst by a tree arg-max (no ordering
-              // is needed here: the merge kernel sorts; rows with s >= theta are exactly the rejected ones)
-              my_row[imax * ET] = my_qc[i * ET];
-              float mv[KP];
-              int mi[KP];
+          if (fminf(min3(mg[0], mg[1], mg[2]), mg[3]) < theta) {
+            uint32_t cnt = 0;
 #pragma unroll
-              for (int t2 = 0; t2 < KP; ++t2) {
-                sc[t2] = (t2 == imax) ? s : sc[t2];
-                mv[t2] = sc[t2];
-                mi[t2] = t2;
-              }
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const int j = seg * 16 + g4 * 4;
+              if (mg[g4] < theta) {
 #pragma unroll
-              for (int w = KP / 2; w >= 1; w >>= 1) {
-#pragma unroll
-                for (int t2 = 0; t2 < w; ++t2) {
-                  const bool gt = mv[t2 + w] > mv[t2];
-                  mv[t2] = gt ? mv[t2 + w] : mv[t2];
-                  mi[t2] = gt ? mi[t2 + w] : mi[t2];
+                for (int e = 0; e < 4; ++e) {
+                  if (sg[g4 * 4 + e] < theta) {
+                    my_qs[cnt * ET] = sg[g4 * 4 + e];
+                    my_qc[cnt * ET] = colw + j + e;
+                    ++cnt;
+                  }
                 }
               }
-              theta = fminf(mv[0], hint);
-              imax = mi[0];
+            }
+#pragma unroll 1
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const float s = my_qs[i * ET];
+              if (s < theta) {
+                // replace the current worst, then find the new worst by a tree arg-max (no ordering
+                // is needed here: the merge kernel sorts; rows with s >= theta are exactly the rejected ones)
+                my_row[imax * ET] = my_qc[i * ET];
+                float mv[KP];
+                int mi[KP];
+#pragma unroll
+                for (int t2 = 0; t2 < KP; ++t2) {
+                  sc[t2] = (t2 == imax) ? s : sc[t2];
+                  mv[t2] = sc[t2];
+                  mi[t2] = t2;
+                }
+#pragma unroll
+                for (int w = KP / 2; w >= 1; w >>= 1) {
+#pragma unroll
+                  for (int t2 = 0; t2 < w; ++t2) {
+                    const bool gt = mv[t2 + w] > mv[t2];
+                    mv[t2] = gt ? mv[t2 + w] : mv[t2];
+                    mi[t2] = gt ? mi[t2 + w] : mi[t2];
+                  }
+                }
+                theta = fminf(mv[0], hint);
+                imax = mi[0];
+              }
             }
           }
           if (seg + 1 < CW / 16) {
