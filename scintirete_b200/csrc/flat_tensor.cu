@@ -551,11 +551,86 @@ __global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __re
     }
     keys[i] = key;
   }
+  // Long lists (small batches spread a query block over ~148 row chunks: thousands of candidates,
+  // of which k'' + 1 matter): radix-select the score of rank k'' (4 passes over the 32 score bits),
+  // move the keys up to that score into a 256-entry buffer and sort only those. Many keys tied at
+  // the boundary (more than the buffer holds) fall through to the full sort below.
+  uint32_t n_sort = n_pad;
+  if (n_pad > 512) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rank, s_cnt, s_total;
+    __shared__ uint64_t buf[256];
+    if (threadIdx.x == 0) {
+      s_prefix = 0;
+      s_rank = kpp;
+      s_cnt = 0;
+    }
+    uint32_t mask = 0;
+    bool all = false;  // fewer than k'' + 1 valid keys: take them all
+    for (int shift = 24; shift >= 0 && !all; shift -= 8) {
+      for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        const uint32_t o = (uint32_t)(key >> 32);
+        if (key != KEY_NONE && (o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        uint32_t part = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) part += hist[lane * 8 + b];
+        uint32_t incl = part;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (uint32_t)o) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t rank = s_rank;
+        const uint32_t excl = incl - part;
+        if (lane == 0) s_total = total;
+        if (rank < total && rank >= excl && rank < incl) {  // the bin of rank `rank` is one of this lane's eight
+          uint32_t cum = excl;
+          for (int b = 0; b < 8; ++b) {
+            const uint32_t h = hist[lane * 8 + b];
+            if (rank < cum + h) {
+              s_prefix = prefix | ((uint32_t)(lane * 8 + b) << shift);
+              s_rank = rank - cum;
+              break;
+            }
+            cum += h;
+          }
+        }
+      }
+      __syncthreads();
+      if (s_rank >= s_total && shift == 24) all = true;  // (only the first pass sees every valid key)
+      mask |= 255u << shift;
+    }
+    const uint32_t vmax = all ? 0xFFFFFFFFu : s_prefix;  // score (ord) of the key of rank k''
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) buf[i] = KEY_NONE;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t key = keys[i];
+      if (key != KEY_NONE && (uint32_t)(key >> 32) <= vmax) {
+        const uint32_t pos = atomicAdd(&s_cnt, 1u);
+        if (pos < 256) buf[pos] = key;
+      }
+    }
+    __syncthreads();
+    if (s_cnt <= 256) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) keys[i] = buf[i];
+      n_sort = 256;
+    }
+  }
   // block bitonic sort (ascending)
-  for (uint32_t size = 2; size <= n_pad; size <<= 1) {
+  for (uint32_t size = 2; size <= n_sort; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
-      for (uint32_t t = threadIdx.x; t < n_pad / 2; t += blockDim.x) {
+      for (uint32_t t = threadIdx.x; t < n_sort / 2; t += blockDim.x) {
         uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
         bool up = ((lo & size) == 0);
         uint64_t x = keys[lo], y = keys[hi];
@@ -568,7 +643,7 @@ __global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __re
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < kpp; i += blockDim.x) {
-    uint64_t key = (i < n_pad) ? keys[i] : KEY_NONE;
+    uint64_t key = (i < n_sort) ? keys[i] : KEY_NONE;
     out_rows[(size_t)q * kpp + i] = (key == KEY_NONE) ? ROW_NONE : (uint32_t)key;
   }
   if (threadIdx.x == 0) {
@@ -577,7 +652,7 @@ __global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __re
     float tau = __int_as_float(0x7f800000);
     for (uint32_t c = 0; c < n_chunks; ++c) tau = fminf(tau, chunk_tau[(size_t)q * n_chunks + c]);
     out_tau_chunks[q] = tau;  // bound on rows no chunk kept: valid when ALL kept candidates are reranked
-    if (kpp < n_pad && keys[kpp] != KEY_NONE) tau = fminf(tau, ord_f32((uint32_t)(keys[kpp] >> 32)));
+    if (kpp < n_sort && keys[kpp] != KEY_NONE) tau = fminf(tau, ord_f32((uint32_t)(keys[kpp] >> 32)));
     out_tau[q] = tau;
   }
 }

@@ -149,3 +149,36 @@ def test_auto_dispatch():
     o = oracle.flat_search(3, db, q, 10, nthreads=8)
     assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
     s.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_small_batch_on_many_rows_selects_candidates_by_radix(metric):
+    # few queries over many rows: the query block is spread over ~148 row chunks, so the merge sees
+    # thousands of candidates per query and takes the radix-select path (k'' + 1 of them matter)
+    n, d, nq, k = 200_000, 64, 3, 10
+    db, q = gaussian(n, d, 21), gaussian(nq, d, 22)
+    s = DeviceStore(d, metric)
+    s.set_option("flat_path", 2)
+    s.append(db)
+    ids, dist, _ = s.search_flat(q, k)
+    c = s.last_counters()
+    s.close()
+    o = oracle.flat_search(int(metric), db, q, k, nthreads=8)
+    assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+    assert c[2] == 0                      # certified without the exact re-scan
+
+
+def test_small_batch_with_mass_ties_falls_back_to_the_full_sort_and_stays_exact():
+    # 150 000 identical rows among 200 000: far more keys tie at the selection boundary than the
+    # select buffer holds -> full sort, certificate refuses, exact re-scan answers
+    n, d, nq, k = 200_000, 64, 2, 10
+    db = gaussian(n, d, 23)
+    db[10_000:160_000] = db[9_999]
+    q = np.stack([db[9_999] + np.float32(1e-3), gaussian(1, d, 24)[0]])
+    s = DeviceStore(d, DistanceMetric.L2)
+    s.set_option("flat_path", 2)
+    s.append(db)
+    ids, dist, _ = s.search_flat(q, k)
+    s.close()
+    o = oracle.flat_search(1, db, q, k, nthreads=8)
+    assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
