@@ -410,7 +410,7 @@ def run_ours(args, wl):
                 flops = 2.0 * nq * n_local * dim
                 ach = flops / (avg_ms * 1e-3) / 1e12
                 # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-                traffic = 2.384e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
+                traffic = 2.387e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
                 roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                         "frac": ach / pk["bf16_sustained"], "traffic": traffic,
                         "traffic_source": "profiles/r01_ncu_tensor_filter_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
@@ -429,7 +429,7 @@ def run_ours(args, wl):
                 ach = byts / (avg_ms * 1e-3) / 1e9
                 # DRAM bytes per launch from the committed ncu --set full capture of this exact workload: BELOW the
                 # algorithmic bytes, because the walks of a batch share hub rows and L2 serves them
-                traffic = 8.726e9 if (rows, dim, nq, world, args.ef) == (1_000_000, 128, 10_000, 1, 128) else None
+                traffic = 8.701e9 if (rows, dim, nq, world, args.ef) == (1_000_000, 128, 10_000, 1, 128) else None
                 roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": ach / pk["hbm"], "traffic": traffic,
                         "traffic_source": "profiles/r01_ncu_hnsw_search_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
