@@ -490,17 +490,47 @@ int32_t scn_store_stats(scn_store* s, scn_stats* out) {
   return SCN_OK;
 }
 
+// rows by index -> dense [n][dim] block (one warp per row), for scn_store_get
+__global__ void __launch_bounds__(256) get_rows_kernel(const float* __restrict__ vec, uint32_t pitch, uint32_t dim,
+                                                       const uint32_t* __restrict__ rows, uint64_t n, float* __restrict__ out) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* src = vec + (uint64_t)rows[warp] * pitch;
+  float* dst = out + warp * dim;
+  for (uint32_t i = lane; i < dim; i += 32) dst[i] = __ldg(src + i);
+}
+
 int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, float* out) {
   if (!s || (!ids && n) || (!out && n)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
   DeviceGuard g(s->device);
   cudaStream_t st = thread_stream(s->device);
+  std::vector<uint32_t> rows(n);
   for (uint64_t i = 0; i < n; ++i) {
-    uint32_t r;
-    if (!s->lookup(ids[i], &r)) return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);
-    SCN_CUDA(cudaMemcpyAsync(out + i * s->dim, s->d_vec + (uint64_t)r * s->pitch, s->dim * sizeof(float),
-                             cudaMemcpyDeviceToHost, st));
+    if (!s->lookup(ids[i], &rows[i])) return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);
   }
-  SCN_CUDA(cudaStreamSynchronize(st));
+  if (n <= 4) {  // HNSW.Get of one vector: straight copies
+    for (uint64_t i = 0; i < n; ++i)
+      SCN_CUDA(cudaMemcpyAsync(out + i * s->dim, s->d_vec + (uint64_t)rows[i] * s->pitch, s->dim * sizeof(float),
+                               cudaMemcpyDeviceToHost, st));
+    SCN_CUDA(cudaStreamSynchronize(st));
+    return SCN_OK;
+  }
+  // result decoration for whole batches (include_vector): gather on the device, one copy per block of rows
+  const uint64_t block_rows = std::max<uint64_t>(1, ((uint64_t)64 << 20) / ((uint64_t)s->dim * sizeof(float)));
+  Scratch scratch(st);
+  uint32_t* d_rows = nullptr;
+  float* d_out = nullptr;
+  SCN_TRY(scratch.alloc(&d_rows, std::min(n, block_rows)));
+  SCN_TRY(scratch.alloc(&d_out, std::min(n, block_rows) * s->dim));
+  for (uint64_t i0 = 0; i0 < n; i0 += block_rows) {
+    const uint64_t m = std::min(block_rows, n - i0);
+    SCN_CUDA(cudaMemcpyAsync(d_rows, rows.data() + i0, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    get_rows_kernel<<<(unsigned)((m * 32 + 255) / 256), 256, 0, st>>>(s->d_vec, s->pitch, s->dim, d_rows, m, d_out);
+    SCN_LAUNCHED();
+    SCN_CUDA(cudaMemcpyAsync(out + i0 * s->dim, d_out, m * s->dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SCN_CUDA(cudaStreamSynchronize(st));
+  }
   return SCN_OK;
 }
 

@@ -165,3 +165,18 @@ def test_vector_index_interface_like_reference_tests():
     with pytest.raises(ScintireteError):
         idx.insert(Vector(1, [1.0, 2.0]))  # duplicate insert
     assert np.array_equal(idx.get("4").elements, np.array([2.0, 2.0], np.float32))
+
+
+def test_get_of_many_ids_gathers_on_the_device():
+    # result decoration (include_vector) for whole batches: rows come back through one device gather
+    # per block of ids; ragged dim (row pitch != dim), repeated and out-of-order ids, unknown id -> 3004
+    n, d = 5000, 33
+    db = gaussian(n, d, 11)
+    s = DeviceStore(d, DistanceMetric.L2)
+    s.append(db)
+    ids = np.random.default_rng(5).integers(1, n + 1, 3000).astype(np.uint64)
+    assert np.array_equal(s.get(ids), db[ids.astype(np.int64) - 1])
+    with pytest.raises(ScintireteError) as e:
+        s.get(np.array([1, 2, 3, 4, 5, n + 7], np.uint64))
+    assert e.value.code == 3004
+    s.close()
