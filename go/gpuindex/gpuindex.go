@@ -407,6 +407,42 @@ func (d GPUDistance) Distance(a, b []float32) float32 {
 func (d GPUDistance) DistanceType() types.DistanceMetric { return d.Metric }
 func (d GPUDistance) IsSimilarity() bool                 { return false }
 
+// The batched forms of the helpers in distance.go:152-192 (NormalizeVector, VectorMagnitude,
+// DotProduct): n vectors of dim floats each, flat; results carry the bits of the Go loops.
+func vectorOps(device int, op C.int32_t, a, b []float32, n, dim int, out []float32) error {
+	if n == 0 {
+		return nil
+	}
+	var pb *C.float
+	if b != nil {
+		pb = (*C.float)(unsafe.Pointer(&b[0]))
+	}
+	return scnErr(C.scn_vector_ops(C.int32_t(device), op, (*C.float)(unsafe.Pointer(&a[0])), pb, C.uint64_t(n),
+		C.uint32_t(dim), (*C.float)(unsafe.Pointer(&out[0]))))
+}
+
+// NormalizeVectors: out[i] = algorithm.NormalizeVector(a[i]); zero vectors come back unchanged.
+func NormalizeVectors(device int, a []float32, n, dim int) ([]float32, error) {
+	out := make([]float32, n*dim)
+	return out, vectorOps(device, C.SCN_VEC_NORMALIZE, a, nil, n, dim, out)
+}
+
+// VectorMagnitudes: out[i] = algorithm.VectorMagnitude(a[i]).
+func VectorMagnitudes(device int, a []float32, n, dim int) ([]float32, error) {
+	out := make([]float32, n)
+	return out, vectorOps(device, C.SCN_VEC_MAGNITUDE, a, nil, n, dim, out)
+}
+
+// DotProducts: out[i] = algorithm.DotProduct(a[i], b[i]); a and b must hold n*dim floats each
+// (the reference's length-mismatch case returns 0 and needs no device call).
+func DotProducts(device int, a, b []float32, n, dim int) ([]float32, error) {
+	out := make([]float32, n)
+	if len(a) != len(b) {
+		return out, nil
+	}
+	return out, vectorOps(device, C.SCN_VEC_DOT, a, b, n, dim, out)
+}
+
 // Factory implements core.IndexFactory (interfaces.go:187-196) for "hnsw-gpu" and "flat-gpu".
 type Factory struct{ Device int }
 

@@ -181,6 +181,19 @@ SCN_API int32_t scn_rerank(scn_store* s, const float* q, uint64_t nq, const uint
 SCN_API int32_t scn_distance_batch(int32_t device, int32_t metric, const float* q, uint64_t nq, const float* x, uint64_t nx,
                            uint32_t dim, float* out);
 
+/* The vector helpers of distance.go:152-192, batched over n vectors of `dim` floats, in the
+ * reference's sequential fp32 order (results are bit-identical to the Go functions):
+ *   SCN_VEC_MAGNITUDE  out[i]       = VectorMagnitude(a_i)            (distance.go:175-181)   out: [n]
+ *   SCN_VEC_NORMALIZE  out[i][...]  = NormalizeVector(a_i); a zero vector comes back unchanged
+ *                                     (distance.go:154-172)                                   out: [n][dim]
+ *   SCN_VEC_DOT        out[i]       = DotProduct(a_i, b_i)            (distance.go:184-192)   out: [n]
+ * b is only read by SCN_VEC_DOT. (DotProduct's length-mismatch case, which returns 0, cannot arise
+ * here: both operands have `dim` elements; the host mirror handles it before calling.) */
+#define SCN_VEC_MAGNITUDE 1
+#define SCN_VEC_NORMALIZE 2
+#define SCN_VEC_DOT 3
+SCN_API int32_t scn_vector_ops(int32_t device, int32_t op, const float* a, const float* b, uint64_t n, uint32_t dim, float* out);
+
 /* ---- search (device buffers; asynchronous on `stream`, a cudaStream_t) ---------------------- */
 SCN_API int32_t scn_search_flat_dev(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t* d_out_ids,
                             float* d_out_dist, uint32_t* d_out_counts, void* stream);

@@ -4,8 +4,9 @@ this package is the tested host-side mirror of the Go cgo shim in go/."""
 from .types import (DistanceMetric, ErrorCode, GraphState, HNSWParams, ScintireteError, SearchParams, SearchResult,
                     Vector)
 from .index import (Batcher, DeviceStore, DistanceCalculator, GPUFlatIndex, GPUHNSWIndex, IndexFactory, batch_distance,
-                    new_distance_calculator)
+                    dot_product, new_distance_calculator, normalize_vector, vector_magnitude)
 
 __all__ = ["DistanceMetric", "ErrorCode", "GraphState", "HNSWParams", "ScintireteError", "SearchParams",
            "SearchResult", "Vector", "Batcher", "DeviceStore", "DistanceCalculator", "GPUFlatIndex", "GPUHNSWIndex",
-           "IndexFactory", "batch_distance", "new_distance_calculator"]
+           "IndexFactory", "batch_distance", "dot_product", "new_distance_calculator", "normalize_vector",
+           "vector_magnitude"]

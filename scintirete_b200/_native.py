@@ -52,6 +52,7 @@ SIGNATURES = {
                                 C.c_void_p, C.c_void_p]),
     "scn_distance_batch": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32,
                                         C.c_void_p]),
+    "scn_vector_ops": (C.c_int32, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "scn_search_flat_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "scn_search_hnsw_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,

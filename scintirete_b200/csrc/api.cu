@@ -197,6 +197,31 @@ int32_t scn_distance_batch(int32_t device, int32_t metric, const float* q, uint6
   return SCN_OK;
 }
 
+int32_t scn_vector_ops(int32_t device, int32_t op, const float* a, const float* b, uint64_t n, uint32_t dim, float* out) {
+  if (op != SCN_VEC_MAGNITUDE && op != SCN_VEC_NORMALIZE && op != SCN_VEC_DOT)
+    return fail(SCN_ERR_INVALID_PARAMETERS, "unknown vector operation %d", op);
+  if (n == 0) return SCN_OK;
+  if (!a || !out || (op == SCN_VEC_DOT && !b)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  DeviceGuard g(device);
+  cudaStream_t st = thread_stream(device);
+  Scratch scratch(st);
+  // dim == 0: magnitude and dot of empty vectors are 0 and an empty vector normalises to itself
+  const uint64_t n_in = n * dim, n_out = (op == SCN_VEC_NORMALIZE) ? n * dim : n;
+  if (n_out == 0) return SCN_OK;
+  float *d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+  SCN_TRY(scratch.alloc(&d_a, std::max<uint64_t>(n_in, 1)));
+  SCN_TRY(scratch.alloc(&d_o, n_out));
+  if (n_in) SCN_CUDA(cudaMemcpyAsync(d_a, a, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (op == SCN_VEC_DOT) {
+    SCN_TRY(scratch.alloc(&d_b, std::max<uint64_t>(n_in, 1)));
+    if (n_in) SCN_CUDA(cudaMemcpyAsync(d_b, b, n_in * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  SCN_TRY(vector_ops(op, d_a, d_b, n, dim, d_o, st));
+  SCN_CUDA(cudaMemcpyAsync(out, d_o, n_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SCN_CUDA(cudaStreamSynchronize(st));
+  return SCN_OK;
+}
+
 int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t nq, float* out_scores) {
   if (!s || !q || !out_scores) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
   if (!tensor_path_supported(s, 10)) return fail(SCN_ERR_INVALID_PARAMETERS, "tensor-core path unsupported for dim=%u", s->dim);

@@ -483,6 +483,37 @@ int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const floa
   return SCN_OK;
 }
 
+// ---- scn_vector_ops: VectorMagnitude / NormalizeVector / DotProduct (distance.go:152-192) --------
+// One thread per vector, the reference's sequential fp32 order (a warp reads 32 different vectors:
+// these are API helpers for small inputs, not a streaming path).
+__global__ void vector_ops_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, uint64_t n, uint32_t dim,
+                                  float* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* v = a + i * dim;
+  if (op == SCN_VEC_DOT) {
+    const float* w = b + i * dim;
+    float p = 0.0f;
+    for (uint32_t j = 0; j < dim; ++j) p = __fadd_rn(p, __fmul_rn(v[j], w[j]));   // distance.go:189-191
+    out[i] = p;
+    return;
+  }
+  const float norm = exact_norm_thread(v, dim);                                     // distance.go:155-159, 176-180
+  if (op == SCN_VEC_MAGNITUDE) {
+    out[i] = norm;
+    return;
+  }
+  float* o = out + i * dim;
+  for (uint32_t j = 0; j < dim; ++j) o[j] = (norm == 0.0f) ? v[j] : __fdiv_rn(v[j], norm);  // distance.go:161-170
+}
+
+int32_t vector_ops(int32_t op, const float* d_a, const float* d_b, uint64_t n, uint32_t dim, float* d_out, cudaStream_t stream) {
+  if (n == 0) return SCN_OK;
+  vector_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(op, d_a, d_b, n, dim, d_out);
+  SCN_LAUNCHED();
+  return SCN_OK;
+}
+
 // ---- K7: merge of G per-shard lists [G][nq][k] ---------------------------------------------------
 // One warp per query. Keys carry the global row, so ascending key order is exactly the flat
 // oracle's (distance, row) order over the whole database. ids ride along.

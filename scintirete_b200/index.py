@@ -86,6 +86,43 @@ def batch_distance(calc: DistanceCalculator, query, targets) -> np.ndarray:
     return calc.pairwise(_f32(query)[None, :], t)[0]
 
 
+# The vector helpers of distance.go:152-192 on the GPU, bit-identical to the Go functions. One
+# vector ([dim]) or a batch ([n][dim]) per call.
+_VEC_MAGNITUDE, _VEC_NORMALIZE, _VEC_DOT = 1, 2, 3
+
+
+def _vector_ops(op: int, a, b=None, device: int = 0) -> np.ndarray:
+    a = _f32(a)
+    single = a.ndim == 1
+    a2 = a[None, :] if single else a
+    n, dim = a2.shape
+    b2 = None
+    if b is not None:
+        b2 = _f32(b)
+        b2 = b2[None, :] if b2.ndim == 1 else b2
+    out = np.empty((n, dim) if op == _VEC_NORMALIZE else (n,), np.float32)
+    _check(_native.lib().scn_vector_ops(device, op, _ptr(a2), _ptr(b2), n, dim, _ptr(out)))
+    return out[0] if single else out
+
+
+def normalize_vector(vector, device: int = 0) -> np.ndarray:
+    """algorithm.NormalizeVector (distance.go:154-172): a zero vector is returned unchanged."""
+    return _vector_ops(_VEC_NORMALIZE, vector, device=device)
+
+
+def vector_magnitude(vector, device: int = 0):
+    """algorithm.VectorMagnitude (distance.go:175-181)."""
+    return _vector_ops(_VEC_MAGNITUDE, vector, device=device)
+
+
+def dot_product(a, b, device: int = 0):
+    """algorithm.DotProduct (distance.go:184-192): vectors of different lengths give 0."""
+    a, b = _f32(a), _f32(b)
+    if a.shape != b.shape:
+        return np.float32(0.0)
+    return _vector_ops(_VEC_DOT, a, b, device=device)
+
+
 # ---- device store ------------------------------------------------------------------------------
 
 class DeviceStore:

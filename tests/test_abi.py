@@ -18,7 +18,7 @@ def _declared():
 def test_header_declares_expected_surface():
     names = _declared()
     for must in ("scn_store_create", "scn_store_append", "scn_store_mark_deleted", "scn_graph_upload",
-                 "scn_search_flat", "scn_search_hnsw", "scn_rerank", "scn_distance_batch", "scn_merge_topk_dev",
+                 "scn_search_flat", "scn_search_hnsw", "scn_rerank", "scn_distance_batch", "scn_vector_ops", "scn_merge_topk_dev",
                  "scn_last_error"):
         assert must in names
 

@@ -180,3 +180,45 @@ def test_get_of_many_ids_gathers_on_the_device():
         s.get(np.array([1, 2, 3, 4, 5, n + 7], np.uint64))
     assert e.value.code == 3004
     s.close()
+
+
+# ---- distance.go:152-192 helpers -----------------------------------------------
+
+@pytest.mark.parametrize("v,want", [([1, 0], [1, 0]), ([3, 4], [0.6, 0.8]), ([0, 0], [0, 0]),
+                                    ([-1, 1], [-1 / np.sqrt(np.float32(2)), 1 / np.sqrt(np.float32(2))])])
+def test_normalize_vector_golden_rows(v, want):          # distance_test.go:312-366
+    from scintirete_b200 import normalize_vector, vector_magnitude
+    got = normalize_vector(v)
+    assert np.all(np.abs(got - np.array(want, np.float32)) <= 1e-6)
+    assert np.array_equal(got, oracle.normalize(v))
+    if any(v):
+        assert abs(float(vector_magnitude(got)) - 1.0) <= 1e-6
+
+
+@pytest.mark.parametrize("v,want", [([1, 0], 1.0), ([3, 4], 5.0), ([0, 0, 0], 0.0), ([-1, -1], float(np.sqrt(2.0)))])
+def test_vector_magnitude_golden_rows(v, want):          # distance_test.go:368-409
+    from scintirete_b200 import vector_magnitude
+    assert abs(float(vector_magnitude(v)) - want) <= 1e-6
+    assert vector_magnitude(v) == oracle.magnitude(v)
+
+
+@pytest.mark.parametrize("a,b,want", [([1, 0], [0, 1], 0.0), ([1, 2, 3], [1, 2, 3], 14.0), ([1, -2, 3], [4, 5, 6], 12.0),
+                                      ([1, 2], [1, 2, 3], 0.0)])
+def test_dot_product_golden_rows(a, b, want):            # distance_test.go:411-451 (length mismatch -> 0)
+    from scintirete_b200 import dot_product
+    assert float(dot_product(a, b)) == want
+
+
+def test_vector_helpers_batched_bit_exact():
+    # batches of random vectors, ragged dim: every result carries the bits of the scalar Go loop;
+    # the store's precomputed ||x|| (cosine's normB) is the same VectorMagnitude
+    from scintirete_b200 import dot_product, normalize_vector, vector_magnitude
+    n, d = 700, 257
+    a, b = gaussian(n, d, 31), gaussian(n, d, 32)
+    a[5] = 0                                              # zero vector: returned unchanged, magnitude 0
+    mag, nrm, dot = vector_magnitude(a), normalize_vector(a), dot_product(a, b)
+    for i in range(n):
+        assert mag[i] == oracle.magnitude(a[i])
+        assert dot[i] == oracle.dot(a[i], b[i])
+        assert np.array_equal(nrm[i], oracle.normalize(a[i]))
+    assert np.array_equal(nrm[5], a[5]) and mag[5] == 0
