@@ -226,6 +226,7 @@ static void free_graph(scn_store* s) {
   s->entry_id = 0;
   s->entry_row = ROW_NONE;
   s->graph_nodes = s->graph_edges = s->upper_lists = 0;
+  s->h_node_layer.clear();
 }
 
 extern "C" {
@@ -418,6 +419,25 @@ int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
   }
   SCN_CUDA(cudaMemcpyAsync(s->d_deleted, bits.data(), words * 4, cudaMemcpyHostToDevice, st));
   SCN_CUDA(cudaStreamSynchronize(st));
+  // hnsw.go:280-283: the entry point was deleted -> findNewEntrypoint (617-634): the live node with
+  // the highest getNodeLayer becomes the entry point and its layer the new maxLayer. (The reference
+  // walks a Go map, i.e. ties fall in random order; here, as in the oracle, in insertion order.)
+  if (s->has_graph && s->entry_row != ROW_NONE && ((bits[s->entry_row >> 5] >> (s->entry_row & 31)) & 1u)) {
+    int best = -1;
+    uint32_t best_row = ROW_NONE;
+    const uint64_t n_graph = std::min<uint64_t>(s->graph_nodes, s->h_node_layer.size());
+    for (uint64_t r = 0; r < n_graph; ++r) {
+      if ((bits[r >> 5] >> (r & 31)) & 1u) continue;
+      if ((int)s->h_node_layer[r] > best) {
+        best = s->h_node_layer[r];
+        best_row = (uint32_t)r;
+      }
+    }
+    s->entry_row = best_row;
+    s->max_layer = best;
+    s->entry_id = 0;
+    if (best_row != ROW_NONE) SCN_CUDA(cudaMemcpy(&s->entry_id, s->d_ids + best_row, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
   // the tensor filter learns about deletions through its per-row additive term (+Inf)
   return mark_aux_deleted(s, rows.data(), (uint32_t)rows.size(), st);
 }
@@ -563,11 +583,13 @@ int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t en
   }
   if (upper >= 0xFFFFFFFFull) return fail(SCN_ERR_RESOURCE, "too many upper-layer lists");
   std::vector<uint32_t> adj_up((size_t)upper * su, ROW_NONE);
+  std::vector<uint8_t> node_layer(n, 0);
   uint64_t li = 0, ei = 0, total_edges = 0;
   for (uint64_t i = 0; i < n_nodes; ++i) {
     uint32_t r = node_row[i];
     for (int l = 0; l < list_counts[i]; ++l) {
       uint32_t c = edge_counts[li++];
+      if (c > 0) node_layer[r] = (uint8_t)l;  // highest non-empty layer wins (lists come in layer order)
       uint32_t cap_l = (l == 0) ? s0 : su;
       if (c > cap_l)
         return fail(SCN_ERR_INVALID_PARAMETERS, "node %llu layer %d has %u neighbours (max %u)",
@@ -603,6 +625,7 @@ int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t en
   SCN_CUDA(cudaMemcpy(s->d_up_off, up_off.data(), up_off.size() * 4, cudaMemcpyHostToDevice));
   SCN_CUDA(cudaMemcpy(s->d_adj_up, adj_up.data(), adj_up.size() * 4, cudaMemcpyHostToDevice));
   s->has_graph = true;
+  s->h_node_layer.swap(node_layer);
   s->m = m;
   s->max_layer = max_layer;
   s->entry_id = entry_id;

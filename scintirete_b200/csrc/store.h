@@ -53,6 +53,9 @@ struct scn_store {
   uint64_t entry_id = 0;
   uint32_t entry_row = scn::ROW_NONE;
   uint64_t graph_nodes = 0, graph_edges = 0, upper_lists = 0;
+  // host: highest layer on which a row has at least one edge (getNodeLayer, hnsw.go:472-484), kept
+  // so that a deleted entry point can be replaced like findNewEntrypoint does (hnsw.go:617-634)
+  std::vector<uint8_t> h_node_layer;
   uint32_t* d_adj0 = nullptr;
   uint8_t* d_levels = nullptr;
   uint32_t* d_up_off = nullptr;

@@ -176,3 +176,22 @@ def test_repeated_neighbours_are_dropped_at_upload_like_visited_rows():
     a = g.search_batch(q, SearchParams(top_k=5, ef_search=32))
     b = g2.search_batch(q, SearchParams(top_k=5, ef_search=32))
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_deleting_the_entry_point_picks_a_new_one_like_the_reference():
+    # hnsw.go:280-283 + findNewEntrypoint (617-634): the live node with the highest getNodeLayer
+    # takes over and its layer becomes maxLayer (ties: insertion order, as in the oracle; the Go map
+    # order is random). Walks after the hand-over stay identical — three hand-overs in a row.
+    n, d = 4000, 32
+    db, h, g = _pair(DistanceMetric.L2, n, d, efc=100)
+    q = gaussian(120, d, 17)
+    for _ in range(3):
+        ep = h.entrypoint()
+        h.delete(int(ep))
+        g.delete(str(int(ep)))
+        assert h.entrypoint() != ep and g.store.stats().entry_id == h.entrypoint()
+        assert g.get_layers() == h.max_layer() + 1
+        o_ids, o_dist, o_cnt, _ = h.search_batch(q, 10, 64, nthreads=4)
+        ids, dist, cnt = g.search_batch(q, SearchParams(top_k=10, ef_search=64))
+        assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist)
+        assert not np.isin(ids, [ep]).any()
