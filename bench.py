@@ -39,6 +39,7 @@ WORKLOADS = {
     "c2-small": (100_000, 768, 2, 2_000, 10, "flat"),
     "c1": (100_000, 128, 1, 1_000, 10, "hnsw"),        # configs[0]
     "c3": (1_000_000, 128, 1, 10_000, 10, "hnsw"),     # configs[2]
+    "c1-768": (100_000, 768, 2, 10_000, 10, "hnsw"),   # embedding-sized rows (cosine): the two-stage row gather
 }
 METRIC_NAME = {1: "L2", 2: "cosine", 3: "inner_product"}
 SEED_DB, SEED_Q = 1234, 4321
