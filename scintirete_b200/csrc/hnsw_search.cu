@@ -10,15 +10,23 @@
 //                      trigger the `break` at hnsw.go:516-518), so "pop the closest of C" is "take
 //                      the first un-expanded entry of W" and the loop ends when there is none.
 //                      (Only exact float ties with W[ef-1] can make the two differ.)
-//   visited         -> open-addressing hash of row indices in shared memory (global-memory table
-//                      as the overflow pass)
-//   Distance()      -> one lane per neighbour: the lane walks its neighbour's row with 128-bit
-//                      loads and accumulates in the reference's exact sequential fp32 order, so all
-//                      (up to 32) neighbours of an expansion are evaluated concurrently, their loads
-//                      overlap, and every distance — hence the whole walk — is bit-identical to the
-//                      reference's. (The first version evaluated 4 rows at a time warp-cooperatively
-//                      with shuffle reductions and serialised ~6 memory latencies per expansion:
-//                      25 us per expansion at C1.)
+//   visited         -> open-addressing table of row indices, groups of four 32-bit slots, private
+//                      to the warp: in GLOBAL memory (L2-resident) by default, because the table
+//                      was what limited the number of resident queries, with a warp-collective,
+//                      atomic-free insert and group snapshots fetched ahead for the predicted next
+//                      expansion (visited_insert_warp); in shared memory with a CAS insert as the
+//                      alternative (option hnsw_global=0). A table that fills up sends the query to
+//                      an overflow pass with an 8x table.
+//   Distance()      -> one lane per neighbour: the lane walks its neighbour's row in the reference's
+//                      exact sequential fp32 order, so all (up to 32) neighbours of an expansion are
+//                      evaluated concurrently and every distance — hence the whole walk — is
+//                      bit-identical to the reference's. The rows reach the lanes through shared
+//                      memory (warp-wide cp.async, one 128-byte line of four rows per instruction,
+//                      requested BEFORE the visited test so that the copies fly while the table is
+//                      probed; common.cuh gather_*), or through registers (LDG.256, option
+//                      hnsw_gather=0). (The first version evaluated 4 rows at a time
+//                      warp-cooperatively with shuffle reductions and serialised ~6 memory latencies
+//                      per expansion: 25 us per expansion at C1.)
 //   admission       -> the reference admits neighbours one by one against the current W[ef-1]
 //                      (strict <) and re-sorts; the result is the best ef of W u new under the
 //                      stable (dist, admission order) order, which is computed here in one step:
@@ -27,7 +35,9 @@
 // not traversed) -> mark visited -> distance -> admit if |W| < ef or d < W[ef-1].d (strict).
 // The rerank of hnsw.go:317-347 recomputes the same distances and stably re-sorts an already
 // sorted list, so the first min(k, |W|) entries of W are the result.
-// Roofline: HBM random gather; algorithmic bytes per query = evals*dim*4 + hops*2M*4.
+// Roofline: HBM random gather; algorithmic bytes per query = evals*dim*4 + hops*2M*4. In practice
+// the walk is a chain of dependent round trips: throughput = resident queries / per-expansion
+// latency (DESIGN.md 4.2 has the measurements behind every choice above).
 #include "store.h"
 
 namespace scn {
@@ -594,11 +604,12 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   a.s0 = 2 * (uint32_t)s->m;
   a.su = (uint32_t)s->m;
   a.has_deleted = (s->live != s->rows) ? 1u : 0u;
-  // gather mode (see gm_ch): rows longer than 512 bytes take two 512-byte stages
+  // gather mode (see gm_ch). Auto: the smallest stage layout (most resident queries) for rows of up
+  // to 512 bytes; longer rows: see opt_hnsw_gather_long.
   int gm = (int)s->opt_hnsw_gather;
-  if (gm < 0 || gm > 3) gm = 1;
-  if (gm != 0 && a.pitch * 4 > 512) gm = 2;
-  if (gm == 2 && a.pitch * 4 <= 512) gm = 1;
+  if (gm < 0 || gm > 3) gm = (a.pitch * 4 > 512) ? (int)s->opt_hnsw_gather_long : 3;
+  if (gm < 0 || gm > 3) gm = 2;
+  if (gm == 2 && a.pitch * 4 <= 512) gm = 1;  // a single stage needs no second buffer
   a.global_first = s->opt_hnsw_global ? 1u : 0u;
   a.early_issue = s->opt_hnsw_early ? 1u : 0u;
   a.max_per_sm = (uint32_t)std::max<int64_t>(0, s->opt_hnsw_per_sm);

@@ -648,6 +648,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_overfetch = value;
   } else if (n == "hnsw_gather") {
     s->opt_hnsw_gather = value;
+  } else if (n == "hnsw_gather_long") {
+    s->opt_hnsw_gather_long = value;
   } else if (n == "hnsw_global") {
     s->opt_hnsw_global = value;
   } else if (n == "hnsw_per_sm") {
