@@ -66,7 +66,7 @@ struct scn_store {
   int64_t opt_tensor_min_batch = 1;  // the bf16 filter streams half the bytes of the fp32 scan: it wins at every batch size
   int64_t opt_overfetch = 0;  // 0 = auto
   int64_t opt_hnsw_gather = -1;   // hnsw_search row gather: -1 auto; 0 registers (LDG.256); 1 <512,1>, 2 <512,2>, 3 <256,1> shared-memory stages
-  int64_t opt_hnsw_gather_long = 2;  // the auto choice for rows longer than 512 bytes
+  int64_t opt_hnsw_gather_long = 1;  // the auto choice for rows longer than 512 bytes (C1-768: <512,1> 21.9 ms / 2.9 ms at nq = 10 000 / 1 000; <512,2> 22.5 / 3.1; <256,1> 21.2 / 3.6)
   int64_t opt_hnsw_global = 1;    // hnsw_search: 1 = visited tables of the first pass in global memory (L2) instead of shared memory
   int64_t opt_hnsw_per_sm = 0;    // hnsw_search, global tables: cap on resident queries per SM; 0 = whatever fits
   int64_t opt_hnsw_early = 1;     // hnsw_search: rows requested before the visited test (copies overlap the probes)
