@@ -71,7 +71,7 @@ struct scn_store {
   int64_t opt_hnsw_per_sm = 0;    // hnsw_search, global tables: cap on resident queries per SM; 0 = whatever fits
   int64_t opt_hnsw_early = 1;     // hnsw_search: rows requested before the visited test (copies overlap the probes)
   int64_t opt_hnsw_rank = 1;      // hnsw_search, global tables: 1 = MATCH.ANY ranks the lanes of a group, 0 = shuffles
-  int64_t opt_hnsw_hash = 0;      // hnsw_search: entries of the shared-memory visited table; 0 = auto
+  int64_t opt_hnsw_hash = 0;      // hnsw_search: entries of the visited table of the first pass (shared or global memory); 0 = auto
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
