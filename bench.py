@@ -204,7 +204,7 @@ def run_reference(args, wl):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -480,7 +480,7 @@ def run_ours(args, wl):
             "kernels_ms_per_step": {n_: v[0] / args.steps for n_, v in timings.items()},
             "counters": counters,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if exchange is not None:
         exchange.status(torch.cuda.current_stream().cuda_stream)   # a missed peer arrival would have invalidated the run
         barrier()
@@ -489,7 +489,27 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: file descriptor 1 is pointed at stderr for
+    everything that writes to it behind Python's back (NCCL prints its version banner there), and
+    the line itself goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
