@@ -68,3 +68,39 @@ def test_key_encoding_is_order_preserving():
     xs = np.array([-np.inf, -3.5, -1e-30, -0.0, 0.0, 1e-30, 2.0, np.inf], np.float32)
     o = [int(ord32(x)) for x in xs]
     assert o == sorted(o) and o[3] == o[4]
+
+
+def test_go_shim_binds_only_declared_entry_points_with_the_declared_arity():
+    # go/gpuindex/gpuindex.go cannot be compiled here (no Go toolchain): at least every C.scn_* call
+    # in it must name an entry point of include/scn_gpu.h and pass as many arguments as it declares
+    header = open(os.path.join(ROOT, "include", "scn_gpu.h")).read()
+    go = open(os.path.join(ROOT, "go", "gpuindex", "gpuindex.go")).read()
+
+    def split_args(text, start):          # text[start] == '(' -> top-level comma count of the call
+        depth, n, i, any_char = 0, 0, start, False
+        while i < len(text):
+            ch = text[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n + (1 if any_char else 0)
+            elif ch == "," and depth == 1:
+                n += 1
+            elif depth >= 1 and not ch.isspace():
+                any_char = True
+            i += 1
+        raise AssertionError("unbalanced call")
+
+    declared = {}
+    header_nc = re.sub(r"/\*.*?\*/", "", header, flags=re.S)   # arity without the comments inside signatures
+    for m in re.finditer(r"SCN_API\s+[\w\s\*]+?\b(scn_\w+)\s*\(", header_nc):
+        args = header_nc[m.end():header_nc.index(")", m.end())]
+        declared[m.group(1)] = 0 if args.strip() in ("", "void") else args.count(",") + 1
+    calls = list(re.finditer(r"\bC\.(scn_\w+)\s*\(", go))
+    assert len(calls) >= 15
+    for m in calls:
+        name = m.group(1)
+        assert name in declared, f"{name} is not declared in scn_gpu.h"
+        assert split_args(go, m.end() - 1) == declared[name], f"{name}: argument count differs from the header"
