@@ -249,9 +249,19 @@ SCN_API int32_t scn_batcher_search(scn_batcher* b, const float* q, uint32_t k, u
 SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
 
 /* ---- tuning / introspection ---------------------------------------------------------------- */
-/* Options: "flat_path" 0 = auto, 1 = exact CUDA-core scan only, 2 = tensor-core filter + exact
- * rerank; "tensor_min_batch" (auto crossover); "overfetch" (candidates kept per query and column
- * block by the tensor filter); "profile" 1 = record per-kernel CUDA-event timings. */
+/* Options (defaults are the measured best; the alternatives are kept as switches for comparison and
+ * are covered by the parity tests — none of them changes a result):
+ *   "flat_path"         0 = auto, 1 = exact CUDA-core scan only, 2 = tensor-core filter + exact rerank
+ *   "tensor_min_batch"  smallest batch that takes the tensor-core filter (default 1)
+ *   "overfetch"         candidates kept per query and column block by the tensor filter (0 = auto)
+ *   "tensor_hint"       1 = lists of a query start from the threshold of the finished ones (default)
+ *   "tensor_bn"         128 forces 128-row tiles (0 = auto); "tensor_chunks" row chunks per query block (0 = auto)
+ *   "hnsw_gather"       row gather of hnsw_search: -1 auto, 0 registers (LDG.256), 1 / 2 / 3 shared-memory
+ *                       stages of 512 B / 2 x 512 B / 256 B; "hnsw_gather_long" the auto choice for rows > 512 B
+ *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory
+ *   "hnsw_hash"         entries of the visited table (0 = auto); "hnsw_per_sm" cap on resident queries per SM
+ *   "hnsw_early"        1 = rows requested before the visited test (default); "hnsw_rank" 1 = MATCH.ANY slot ranking
+ *   "profile"           1 = record per-kernel CUDA-event timings and the device counters */
 SCN_API int32_t scn_set_option(scn_store* s, const char* name, int64_t value);
 /* Per-kernel CUDA-event timings accumulated since the previous call (option "profile" = 1):
  * names[i] -> total ms[i] over counts[i] launches. Synchronises on the recorded events, then
