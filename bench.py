@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py — queries/sec of the search hot path on B200 (see BASELINE.json / SURVEY.md §8d).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|hnsw|...]
-    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c3|...]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1: one rank per GPU)
 
 A "step" is one pass of the hot path over one batch of synthetic queries. Default workload (C2):
-1M x 768 fp32 Gaussian rows, cosine, exact k=10 search of a 10 000-query batch on one B200. With
-N > 1 the same database is row-sharded over the ranks (strong scaling); every rank scans its shard
-for the whole batch, the per-shard top-k lists are all-gathered over NCCL and merged by
-scn_merge_topk_dev.
+1M x 768 fp32 Gaussian rows, cosine, exact k=10 search of a 10 000-query batch. With N > 1 the same
+database is row-sharded over the ranks (strong scaling); a batch is cut into N query slices, every
+rank scans its rows for the whole batch and answers its slice (fused exchange over NVLink peer
+memory, csrc/exchange.cu; `--merge nccl` = the NCCL all-gather formulation for comparison).
 
 Printed JSON line: `value` = queries/s with the queries already resident in HBM (CUDA events on
 the launching stream, max over ranks); `e2e` = queries/s through the blocking host-buffer C-ABI call
-(pinned host queries in, ids/distances out, copies inside the timed region); `roofline` for the
-dominant kernel from live CUDA-event timings; `cpu_baseline` = the CPU oracle (restatement of the
-reference's Go code; "port") timed on this box's host cores on a bounded query sample.
+(pinned host buffers from scn_host_alloc; copies inside the timed region; `pageable` = the same call
+from ordinary pageable memory); `roofline` for the dominant kernel from live CUDA-event timings;
+`cpu_baseline` = the CPU oracle (restatement of the reference's Go code; "port") timed on this box's
+host cores on a bounded query sample; `verified` = a query sample of the results compared with the
+oracle over the same rows (ids and distance bits). `secondary` carries the other BASELINE.json
+configurations measured in the same run: C3 (HNSW, N = 1; recall and an ef sweep), C4 (N >= 2).
 """
 from __future__ import annotations
 
@@ -52,6 +55,18 @@ def peaks():
         return {"hbm": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
                 "source": "measured"}
     return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+def traffic_for(kernel: str, rows: int, dim: int, nq: int, world: int, ef=None):
+    """DRAM bytes per launch of `kernel` on exactly this configuration, from the committed
+    `ncu --set full` captures (profiles/traffic.json: one entry per capture, with its source file).
+    None when this configuration was never captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    key = f"{kernel}|rows={rows}|dim={dim}|nq={nq}|world={world}" + (f"|ef={ef}" if ef is not None else "")
+    e = json.load(open(p)).get(key)
+    return (e["bytes"], e["source"]) if e else (None, None)
 
 
 class ClockSampler(threading.Thread):
@@ -101,7 +116,7 @@ class ClockSampler(threading.Thread):
 
 
 def gen_rows_numpy(row0: int, n: int, dim: int, seed: int) -> np.ndarray:
-    """Host generator (reference arm / CPU baseline): block-seeded so any row range is reproducible."""
+    """Host generator (reference arm / HNSW workloads): block-seeded so any row range is reproducible."""
     out = np.empty((n, dim), np.float32)
     blk = 65536
     r = row0
@@ -114,16 +129,19 @@ def gen_rows_numpy(row0: int, n: int, dim: int, seed: int) -> np.ndarray:
     return out
 
 
+def graph_cache_path(n, dim, metric, M=16, efc=200, seed=42):
+    return os.path.join(ROOT, "bench_cache", f"hnsw_n{n}_d{dim}_m{metric}_M{M}_efc{efc}_s{seed}_db{SEED_DB}.npz")
+
+
 def hnsw_graph_cached(db: np.ndarray, metric: int, ef_search: int, M: int = 16, efc: int = 200, seed: int = 42):
     """The graph the reference's algorithm builds (serial CPU construction, hnsw.go:148-257, restated
     by the oracle). Built once per (data, parameters) and cached under bench_cache/ because the
-    serial build takes minutes (100k x 128) to an hour (1M x 128) on one core; the cache travels to
+    serial build takes minutes (100k x 128) to hours (1M x 128) on one core; the cache travels to
     the GPU box with the repo snapshot. Returns (oracle index, build seconds or None if cached)."""
     import oracle
 
     n, dim = db.shape
-    tag = f"hnsw_n{n}_d{dim}_m{metric}_M{M}_efc{efc}_s{seed}_db{SEED_DB}"
-    path = os.path.join(ROOT, "bench_cache", tag + ".npz")
+    path = graph_cache_path(n, dim, metric, M, efc, seed)
     h = oracle.OracleHNSW(M=M, ef_construction=efc, ef_search=ef_search, max_layers=16, seed=seed, metric=metric)
     if os.path.exists(path):
         z = np.load(path)
@@ -178,8 +196,6 @@ def run_reference(args, wl):
         qps = args.steps * per_step / dt
         sample = f"{per_step} queries/step x {args.steps} steps over the full {rows}x{dim} database, one query per thread"
     else:
-        import oracle
-
         db = gen_rows_numpy(0, rows, dim, SEED_DB)
         q = gen_rows_numpy(0, nq, dim, SEED_Q)
         h, _ = hnsw_graph_cached(db, metric, args.ef)
@@ -211,282 +227,527 @@ def run_reference(args, wl):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
-def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide pieces shared by the workloads of one run."""
 
-    from scintirete_b200 import DeviceStore, DistanceMetric, _native
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        from scintirete_b200 import _native
+
+        self.args, self.torch, self.dist = args, torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torchrun --nproc-per-node {args.gpus}")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _native.lib()
+        self.peaks = peaks()
+        self.threads = os.cpu_count() or 1
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def time_device(ctx: Ctx, step, steps: int, warmup: int, store):
+    """W warm-ups, then K steps bracketed by barrier + synchronize, CUDA events on the launching
+    stream, max over ranks. Per-kernel event timings are collected during the timed steps."""
+    torch = ctx.torch
+    store.set_option("profile", 0)
+    for _ in range(warmup):
+        step()
+    store.set_option("profile", 1)
+    store.last_timings()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    launches0 = ctx.lib.scn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    ctx.barrier()
+    launches = ctx.lib.scn_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = ctx.max_over_ranks(e0.elapsed_time(e1))
+    timings = store.last_timings()
+    counters = store.last_counters()
+    store.set_option("profile", 0)
+    return ms_total, timings, counters, int(launches), clocks
+
+
+def time_host(ctx: Ctx, step, steps: int, warmup: int) -> float:
+    """Wall clock around blocking host-buffer calls, max over ranks (seconds for `steps` calls)."""
+    for _ in range(max(1, warmup)):
+        step()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ctx.torch.cuda.synchronize()
+    return ctx.max_over_ranks(time.perf_counter() - t0)
+
+
+def pick_peak(pk, clocks, kind):
+    """Tensor roofline denominator chosen by the clock record of the timed region: the burst figure
+    when the SMs held (nearly) their maximum clock and no power cap was reported, else the sustained one."""
+    if kind == "hbm":
+        return pk["hbm"], pk["source"]
+    capped = "sw_power_cap" in (clocks.get("reasons") or [])
+    held = clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"]
+    if held and not capped:
+        return pk["bf16_burst"], pk["source"] + " (burst bf16: clocks held, no power cap)"
+    return pk["bf16_sustained"], pk["source"] + " (sustained bf16: power-capped or clocks below max)"
+
+
+def roofline_of(ctx: Ctx, timings, counters, clocks, *, rows, n_local, dim, metric, nq, world, ef=None):
+    if not timings:
+        return None
+    pk = ctx.peaks
+    name, (tot_ms, cnt) = max(timings.items(), key=lambda kv: kv[1][0])
+    avg_ms = tot_ms / max(cnt, 1)
+    share = tot_ms / max(sum(v[0] for v in timings.values()), 1e-9)
+    if name == "tensor_filter":
+        flops = 2.0 * nq * n_local * dim
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        peak, src = pick_peak(pk, clocks, "tensor")
+        traffic, tsrc = traffic_for(name, rows, dim, nq, world)
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "frac_sustained": ach / pk["bf16_sustained"], "frac_burst": ach / pk["bf16_burst"], "traffic": traffic,
+                "traffic_source": tsrc, "algorithmic_flop": flops, "peak_source": src, "launch_ms": avg_ms, "share_of_step": share}
+    if name == "flat_exact_scan":
+        passes = (nq + 7) // 8
+        byts = float(passes) * n_local * (dim * 4 + (4 if metric == 2 else 0))
+        ach = byts / (avg_ms * 1e-3) / 1e9
+        traffic, tsrc = traffic_for(name, rows, dim, nq, world)
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": traffic, "traffic_source": tsrc, "peak_source": pk["source"], "launch_ms": avg_ms,
+                "share_of_step": share, "note": f"{passes} passes of 8 queries over fp32 rows per launch"}
+    if name.startswith("hnsw_search") and counters:
+        evals, hops = counters[0], counters[1]
+        byts = evals * dim * 4.0 + hops * 32 * 4.0
+        ach = byts / (avg_ms * 1e-3) / 1e9
+        # DRAM bytes per launch (ncu --set full of this exact workload): the walks of a batch share hub rows
+        # that L2 serves, and the visited tables add traffic the algorithm does not count — report both
+        traffic, tsrc = traffic_for("hnsw_search", rows, dim, nq, world, ef)
+        r = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+             "traffic": traffic, "traffic_source": tsrc, "algorithmic_bytes": byts, "peak_source": pk["source"],
+             "launch_ms": avg_ms, "share_of_step": share,
+             "note": f"{evals / max(nq, 1):.0f} distance evals, {hops / max(nq, 1):.0f} expansions per query (counted on device); "
+                     "algorithmic bytes = evals*dim*4 + expansions*2M*4; the walk is latency-bound (DESIGN.md 4.2)"}
+        if traffic:
+            r["achieved_dram"] = traffic / (avg_ms * 1e-3) / 1e9
+            r["frac_dram"] = r["achieved_dram"] / pk["hbm"]
+        return r
+    return None
+
+
+def oracle_flat_sharded(ctx: Ctx, store, n_local: int, row0: int, qs: np.ndarray, metric: int, k: int):
+    """Exact top-k of the sample queries over the WHOLE database by the CPU oracle: every rank scans
+    the rows its own GPU holds (read back block by block), the per-shard lists are merged by
+    (distance, global row) — the flat oracle's order — on every rank. Returns (ids, dist)."""
+    import oracle
+
+    threads = max(1, ctx.threads // ctx.world)
+    cand_i, cand_d = [], []
+    blk = 131072
+    for lo in range(0, n_local, blk):
+        hi = min(n_local, lo + blk)
+        gids = np.arange(row0 + lo + 1, row0 + hi + 1, dtype=np.uint64)
+        rows = store.get(gids)
+        i_, d_, c_ = oracle.flat_search(metric, rows, qs, k, ids=gids, nthreads=threads)
+        cand_i.append(i_)
+        cand_d.append(d_)
+    if cand_i:
+        li, ld = np.concatenate(cand_i, axis=1), np.concatenate(cand_d, axis=1)
+    else:
+        li, ld = np.zeros((len(qs), 0), np.uint64), np.zeros((len(qs), 0), np.float32)
+    parts = ctx.gather_objects((li, ld))
+    ai = np.concatenate([p[0] for p in parts], axis=1)
+    ad = np.concatenate([p[1] for p in parts], axis=1)
+    out_i = np.zeros((len(qs), k), np.uint64)
+    out_d = np.full((len(qs), k), np.inf, np.float32)
+    for q in range(len(qs)):
+        valid = ai[q] != 0
+        vi, vd = ai[q][valid], ad[q][valid]
+        order = np.lexsort((vi, vd))[:k]            # distance ascending, then id (= global row + 1) ascending
+        out_i[q, :len(order)] = vi[order]
+        out_d[q, :len(order)] = vd[order]
+    return out_i, out_d
+
+
+def bench_flat(ctx: Ctx, wl, name: str, steps: int, warmup: int, cpu_baseline: bool):
+    torch, lib, args = ctx.torch, ctx.lib, ctx.args
+    from scintirete_b200 import DeviceStore, DistanceMetric, PinnedBuffer
     from scintirete_b200.index import _check
 
-    rows, dim, metric, nq, k, kind = wl
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _native.lib()
-
-    store = None
-    if kind == "flat":
-        # ---- row shard of the database, generated on the device ----------------------------------
-        per = (rows + world - 1) // world
-        row0, row1 = rank * per, min(rows, (rank + 1) * per)
-        n_local = row1 - row0
-        store = DeviceStore(dim, DistanceMetric(metric), device=local)
-        store.reserve(n_local)
-        blk = 65536
-        r = row0
-        while r < row1:
-            b = r // blk
-            lo, hi = max(r, b * blk), min(row1, (b + 1) * blk)
-            g = torch.Generator(device=dev)
-            g.manual_seed(SEED_DB * 1_000_003 + b)
-            block = torch.randn((blk, dim), generator=g, device=dev, dtype=torch.float32)
-            chunk = block[lo - b * blk:hi - b * blk].contiguous()
-            store.append_device(chunk.data_ptr(), hi - lo)
-            r = hi
+    rows, dim, metric, nq, k, _ = wl
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    # ---- row shard of the database, generated on the device (global rows row0..row1) ---------------
+    per = (rows + world - 1) // world
+    row0, row1 = min(rows, rank * per), min(rows, (rank + 1) * per)
+    n_local = row1 - row0
+    store = DeviceStore(dim, DistanceMetric(metric), device=local)
+    store.set_option("auto_id_base", row0)          # ids are global row + 1 on every shard
+    store.reserve(n_local)
+    blk = 65536
+    r = row0
+    while r < row1:
+        b = r // blk
+        lo, hi = max(r, b * blk), min(row1, (b + 1) * blk)
         g = torch.Generator(device=dev)
-        g.manual_seed(SEED_Q)
-        q_dev = torch.randn((nq, dim), generator=g, device=dev, dtype=torch.float32)
-        q_host = q_dev.cpu().pin_memory()
-    else:
-        # ---- HNSW: replicas only. Every rank holds the whole store + graph and answers its slice
-        # of the query batch; no data-path collective. Host-generated data (numpy, seeded) so the
-        # cached graph (bench_cache/) matches the vectors bit for bit on any machine. The graph is
-        # the one the reference's algorithm builds (hnsw.go:148-257, restated by the oracle) and
-        # is constructed / loaded outside every timed region.
-        from scintirete_b200 import GraphState
-
-        row0, n_local = 0, rows
-        db_host = gen_rows_numpy(0, rows, dim, SEED_DB)
-        q_all = gen_rows_numpy(0, nq, dim, SEED_Q)
-        qlo, qhi = (nq * rank) // world, (nq * (rank + 1)) // world
-        nq_total, nq = nq, qhi - qlo
-        h, build_s = hnsw_graph_cached(db_host, metric, args.ef)
-        store = DeviceStore(dim, DistanceMetric(metric), device=local)
-        store.append(db_host)
-        st = h.export_graph_state(with_vectors=False)
-        store.graph_upload(GraphState(st.ids, st.list_counts, st.edge_counts, st.edges, st.entrypoint, st.max_layer,
-                                      st.size, m=16))
-        q_host = torch.from_numpy(q_all[qlo:qhi].copy()).pin_memory()
-        q_dev = q_host.to(dev)
+        g.manual_seed(SEED_DB * 1_000_003 + b)
+        block = torch.randn((blk, dim), generator=g, device=dev, dtype=torch.float32)
+        chunk = block[lo - b * blk:hi - b * blk].contiguous()
+        store.append_device(chunk.data_ptr(), hi - lo)
+        r = hi
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED_Q)
+    q_dev = torch.randn((nq, dim), generator=g, device=dev, dtype=torch.float32)   # same batch on every rank
+    q_np = q_dev.cpu().numpy()
+    for kv in args.opt:
+        oname, val = kv.split("=")
+        store.set_option(oname, int(val))
     torch.cuda.synchronize()
 
-    out_ids = torch.zeros((nq, k), dtype=torch.int64, device=dev)
-    out_dist = torch.zeros((nq, k), dtype=torch.float32, device=dev)
-    out_cnt = torch.zeros((nq,), dtype=torch.int32, device=dev)
-    keys = torch.zeros((nq, k), dtype=torch.int64, device=dev)
-    if world > 1:
-        all_keys = torch.zeros((world, nq, k), dtype=torch.int64, device=dev)
-        all_ids = torch.zeros((world, nq, k), dtype=torch.int64, device=dev)
-    h_ids = torch.zeros((nq, k), dtype=torch.int64).pin_memory()
-    h_dist = torch.zeros((nq, k), dtype=torch.float32).pin_memory()
-    h_cnt = torch.zeros((nq,), dtype=torch.int32).pin_memory()
+    def p(t):
+        return C.c_void_p(t.data_ptr())
 
-    # Row-sharded exchange: fused into the search epilogue over NVLink peer memory (P2P stores +
-    # flags, scn_search_flat_exchange_dev), or the NCCL formulation (2 all-gathers + merge).
+    # ---- query slice this rank answers; pinned host buffers for the C-ABI calls -----------------------
     merge_mode, exchange = "none", None
-    if world > 1 and kind == "flat":
+    qlo, qcnt = 0, nq
+    if world > 1:
         merge_mode = args.merge
-        if merge_mode == "p2p":
-            from scintirete_b200.sharding import ShardExchange
+        from scintirete_b200.sharding import ShardExchange, query_slice
 
+        qlo, qhi = query_slice(nq, world, rank)
+        qcnt = qhi - qlo
+        if merge_mode == "p2p":
             handle = None
             try:
-                exchange = ShardExchange(local, rank, world, nq, k)
+                exchange = ShardExchange(local, rank, world, nq, k, dim)
                 handle = exchange.local_handle()
             except Exception as e:
                 print(f"[rank {rank}] peer-memory exchange unavailable ({e})", file=sys.stderr)
-            handles = [None] * world
-            dist.all_gather_object(handles, handle)          # every rank takes part, whatever happened above
-            ok = torch.ones(1, device=dev)
+            handles = ctx.gather_objects(handle)        # every rank takes part, whatever happened above
+            ok = 1.0
             try:
                 if any(h is None for h in handles):
                     raise RuntimeError("a rank could not create its exchange buffer")
                 exchange.connect(handles)
             except Exception as e:  # e.g. CUDA IPC not permitted in this container
                 print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using NCCL all-gather", file=sys.stderr)
-                ok = torch.zeros(1, device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)        # all ranks must agree on the protocol
-            if ok.item() == 0:
+                ok = 0.0
+            if -ctx.max_over_ranks(-ok) == 0.0:           # all ranks must agree on the protocol
                 exchange, merge_mode = None, "nccl"
+    n_out = max(qcnt, 1) if (world > 1 and merge_mode == "p2p") else nq
+    out_ids = torch.zeros((n_out, k), dtype=torch.int64, device=dev)
+    out_dist = torch.zeros((n_out, k), dtype=torch.float32, device=dev)
+    out_cnt = torch.zeros((n_out,), dtype=torch.int32, device=dev)
+    if world > 1 and merge_mode == "nccl":
+        keys = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+        all_keys = torch.zeros((world, nq, k), dtype=torch.int64, device=dev)
+        all_ids = torch.zeros((world, nq, k), dtype=torch.int64, device=dev)
+    n_host_q = max(qcnt, 1) if exchange is not None else nq
+    hq = PinnedBuffer((n_host_q, dim), np.float32)
+    h_ids, h_dist, h_cnt = PinnedBuffer((n_out, k), np.uint64), PinnedBuffer((n_out, k), np.float32), PinnedBuffer((n_out,), np.uint32)
+    if exchange is not None:
+        hq.array[:qcnt] = q_np[qlo:qlo + qcnt]
+    else:
+        hq.array[:] = q_np
+    q_pageable = np.ascontiguousarray(hq.array.copy())
+    pg_ids, pg_dist, pg_cnt = np.zeros((n_out, k), np.uint64), np.zeros((n_out, k), np.float32), np.zeros((n_out,), np.uint32)
+
+    def step_device():
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if world == 1:
+            _check(lib.scn_search_flat_dev(store.handle, p(q_dev), nq, k, p(out_ids), p(out_dist), p(out_cnt), stream))
+        elif exchange is not None:
+            exchange.search(store, q_dev.data_ptr(), nq, row0, out_ids.data_ptr(), out_dist.data_ptr(), out_cnt.data_ptr(),
+                            torch.cuda.current_stream().cuda_stream)
+        else:
+            _check(lib.scn_search_flat_shard_dev(store.handle, p(q_dev), nq, k, row0, p(keys), p(out_ids), stream))
+            ctx.dist.all_gather_into_tensor(all_keys, keys)
+            ctx.dist.all_gather_into_tensor(all_ids, out_ids)
+            _check(lib.scn_merge_topk_dev(local, p(all_keys), p(all_ids), world, nq, k, p(out_ids), p(out_dist),
+                                          p(out_cnt), stream))
+
+    def step_e2e(q_ptr=None, o=None):
+        # the call a user of the C ABI makes: host buffers in, host buffers out, blocking
+        q_ptr = hq.ptr if q_ptr is None else q_ptr
+        oi, od, oc = (h_ids.ptr, h_dist.ptr, h_cnt.ptr) if o is None else o
+        if world == 1:
+            _check(lib.scn_search_flat(store.handle, C.c_void_p(q_ptr), nq, k, C.c_void_p(oi), C.c_void_p(od), C.c_void_p(oc)))
+        elif exchange is not None:
+            exchange.search_host(store, q_ptr, nq, row0, oi, od, oc)
+        else:   # NCCL comparison path: torch copies around the device-buffer entry points
+            q_dev.copy_(torch.from_numpy(hq.array), non_blocking=True)
+            step_device()
+            h_ids.array[:] = out_ids.cpu().numpy().view(np.uint64)
+            h_dist.array[:] = out_dist.cpu().numpy()
+
+    ms_total, timings, counters, launches, clocks = time_device(ctx, step_device, steps, warmup, store)
+    e2e_s = time_host(ctx, step_e2e, steps, max(1, warmup // 2))
+    pageable_s = None
+    if merge_mode != "nccl":
+        pageable_s = time_host(ctx, lambda: step_e2e(q_pageable.ctypes.data, (pg_ids.ctypes.data, pg_dist.ctypes.data, pg_cnt.ctypes.data)),
+                               steps, 1)
+
+    # ---- verification: a sample of this run's results against the CPU oracle over the same rows ----------
+    step_e2e()
+    n_s = min(16 if rows * dim < 4e9 else 8, qcnt if world > 1 else nq, nq)
+    n_s = int(-ctx.max_over_ranks(-float(n_s)))      # the same sample size on every rank (smallest slice)
+    sample_q = np.ascontiguousarray(q_np[:max(n_s, 1)])   # the first queries: rank 0's slice
+    t0 = time.perf_counter()
+    o_ids, o_dist = oracle_flat_sharded(ctx, store, n_local, row0, sample_q, metric, k)
+    verify_s = time.perf_counter() - t0
+    verified = None
+    if rank == 0:
+        same = bool(np.array_equal(h_ids.array[:n_s], o_ids[:n_s]) and np.array_equal(h_dist.array[:n_s], o_dist[:n_s]))
+        same_pg = None if pageable_s is None else bool(np.array_equal(pg_ids[:n_s], o_ids[:n_s]) and np.array_equal(pg_dist[:n_s], o_dist[:n_s]))
+        verified = {"queries": n_s, "identical": same, "identical_pageable_call": same_pg,
+                    "against": f"CPU oracle flat scan over all {rows} rows (each rank scans the rows read back from its own GPU; "
+                               "lists merged by (distance, row)); ids and fp32 distance bits compared",
+                    "seconds": round(verify_s, 1)}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) --------------------------------------------
+    cpu = None
+    if world == 1 and cpu_baseline and rank == 0:
+        threads = ctx.threads
+        db_host = np.concatenate([store.get(np.arange(i, min(i + 65536, n_local), dtype=np.uint64) + 1)
+                                  for i in range(0, n_local, 65536)])
+        ns = min(nq, threads)
+        rounds = 16 if rows * dim >= 5e8 else 32   # about 10 s of host work at C2 (0.6 s per round)
+        qps, dt = cpu_flat_qps(db_host, q_np[:ns], metric, k, threads, rounds)
+        cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+               "sample": f"{ns * rounds} queries ({rounds} rounds x {ns}, one per thread) over the full database, {dt:.1f}s wall"}
+        del db_host
+
+    block = None
+    if rank == 0:
+        ms_step = ms_total / steps
+        roof = roofline_of(ctx, timings, counters, clocks, rows=rows, n_local=n_local, dim=dim, metric=metric, nq=nq, world=world)
+        h2d = (qcnt if exchange is not None else nq) * dim * 4
+        d2h = (qcnt if exchange is not None else nq) * (k * 12 + 4)
+        e2e = {"value": nq * steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "timer": "host wall clock around the blocking host-buffer C-ABI call ("
+                        + ("scn_search_flat" if world == 1 else "scn_search_flat_exchange: this rank's query slice in, its results out"
+                           if exchange is not None else "torch copies + scn_search_flat_shard_dev + NCCL")
+                        + "), pinned buffers (scn_host_alloc); bytes are per rank"}
+        if pageable_s is not None:
+            e2e["pageable"] = {"value": nq * steps / pageable_s, "unit": "queries/s",
+                               "note": "the same call from pageable host memory (a Go slice): staged through the library's pinned chunks"}
+        block = {
+            "workload": f"{name}: {rows}x{dim} {METRIC_NAME[metric]} flat k={k} nq={nq}", "value": nq / (ms_step * 1e-3),
+            "unit": "queries/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+            "dtype": "bf16 filter + f32 exact rerank" if (timings and "tensor_filter" in timings) else "f32",
+            "config": {"workload": f"{name}: {rows}x{dim} {METRIC_NAME[metric]} flat k={k} nq={nq}",
+                       "rows": rows, "dim": dim, "metric": METRIC_NAME[metric], "nq": nq, "k": k, "sharding": f"rows/{world}",
+                       "shard_merge": {"p2p": "fused over NVLink peer memory: query slices gathered and top-k lists sent to the owner of "
+                                              "each query slice as P2P stores + flags; each rank merges its slice",
+                                       "nccl": "NCCL all_gather of keys and ids + merge kernel", "none": None}[merge_mode],
+                       "l2_policy": "database (>= 3 GB fp32 + bf16 mirror per pass) is far larger than the 126 MB L2; no flush needed"
+                       if n_local * dim * 4 > 4e8 else "working set fits L2: flush not applied (small workload, not the headline)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "verified": verified,
+            "kernels_ms_per_step": {n_: v[0] / steps for n_, v in timings.items()}, "counters": counters,
+        }
+    if exchange is not None:
+        ctx.barrier()
+        exchange.close()
+    for b in (hq, h_ids, h_dist, h_cnt):
+        b.close()
+    store.close()
+    del q_dev, out_ids, out_dist, out_cnt
+    torch.cuda.empty_cache()
+    return block
+
+
+def recall_at_k(ids: np.ndarray, gt: np.ndarray) -> float:
+    k = gt.shape[1]
+    return float(np.mean([len(set(ids[i].tolist()) & set(gt[i].tolist())) / k for i in range(len(gt))]))
+
+
+def bench_hnsw(ctx: Ctx, wl, name: str, ef: int, steps: int, warmup: int, cpu_baseline: bool, ef_sweep):
+    """HNSW: replicas only. Every rank holds the whole store + graph and answers its slice of the
+    query batch; no data-path collective. Host-generated data (numpy, seeded) so the cached graph
+    (bench_cache/) matches the vectors bit for bit on any machine. The graph is the one the
+    reference's algorithm builds (hnsw.go:148-257, restated by the oracle), constructed / loaded
+    outside every timed region."""
+    torch, lib = ctx.torch, ctx.lib
+    from scintirete_b200 import DeviceStore, DistanceMetric, GraphState, PinnedBuffer
+    from scintirete_b200.index import _check
+
+    rows, dim, metric, nq_total, k, _ = wl
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    db_host = gen_rows_numpy(0, rows, dim, SEED_DB)
+    q_all = gen_rows_numpy(0, nq_total, dim, SEED_Q)
+    qlo, qhi = (nq_total * rank) // world, (nq_total * (rank + 1)) // world
+    nq = qhi - qlo
+    h, build_s = hnsw_graph_cached(db_host, metric, ef)
+    store = DeviceStore(dim, DistanceMetric(metric), device=local)
+    store.append(db_host)
+    st = h.export_graph_state(with_vectors=False)
+    store.graph_upload(GraphState(st.ids, st.list_counts, st.edge_counts, st.edges, st.entrypoint, st.max_layer, st.size, m=16))
+    for kv in ctx.args.opt:
+        oname, val = kv.split("=")
+        store.set_option(oname, int(val))
+    hq = PinnedBuffer((max(nq, 1), dim), np.float32)
+    hq.array[:nq] = q_all[qlo:qhi]
+    q_dev = torch.from_numpy(hq.array).to(dev)
+    out_ids = torch.zeros((max(nq, 1), k), dtype=torch.int64, device=dev)
+    out_dist = torch.zeros((max(nq, 1), k), dtype=torch.float32, device=dev)
+    out_cnt = torch.zeros((max(nq, 1),), dtype=torch.int32, device=dev)
+    h_ids, h_dist, h_cnt = PinnedBuffer((max(nq, 1), k), np.uint64), PinnedBuffer((max(nq, 1), k), np.float32), PinnedBuffer((max(nq, 1),), np.uint32)
+    torch.cuda.synchronize()
 
     def p(t):
         return C.c_void_p(t.data_ptr())
 
-    def step_device(qd):
+    cur_ef = [ef]
+
+    def step_device():
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        if kind == "hnsw":
-            _check(lib.scn_search_hnsw_dev(store.handle, p(qd), nq, k, args.ef, p(out_ids), p(out_dist), p(out_cnt), stream))
-        elif world == 1 and kind == "flat":
-            _check(lib.scn_search_flat_dev(store.handle, p(qd), nq, k, p(out_ids), p(out_dist), p(out_cnt), stream))
-        elif exchange is not None:
-            exchange.search(store, qd.data_ptr(), nq, row0, out_ids.data_ptr(), out_dist.data_ptr(), out_cnt.data_ptr(),
-                            torch.cuda.current_stream().cuda_stream)
-        else:
-            _check(lib.scn_search_flat_shard_dev(store.handle, p(qd), nq, k, row0, p(keys), p(out_ids), stream))
-            dist.all_gather_into_tensor(all_keys, keys)
-            dist.all_gather_into_tensor(all_ids, out_ids)
-            _check(lib.scn_merge_topk_dev(local, p(all_keys), p(all_ids), world, nq, k, p(out_ids), p(out_dist),
-                                          p(out_cnt), stream))
+        _check(lib.scn_search_hnsw_dev(store.handle, p(q_dev), nq, k, cur_ef[0], p(out_ids), p(out_dist), p(out_cnt), stream))
 
     def step_e2e():
-        # the call a user of the C ABI makes: host buffers in, host buffers out
-        if world == 1 and kind == "flat":
-            _check(lib.scn_search_flat(store.handle, p(q_host), nq, k, p(h_ids), p(h_dist), p(h_cnt)))
-        elif kind == "hnsw":
-            _check(lib.scn_search_hnsw(store.handle, p(q_host), nq, k, args.ef, p(h_ids), p(h_dist), p(h_cnt)))
-        else:
-            q_dev.copy_(q_host, non_blocking=True)
-            step_device(q_dev)
-            h_ids.copy_(out_ids, non_blocking=True)
-            h_dist.copy_(out_dist, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        _check(lib.scn_search_hnsw(store.handle, C.c_void_p(hq.ptr), nq, k, cur_ef[0], C.c_void_p(h_ids.ptr), C.c_void_p(h_dist.ptr),
+                                   C.c_void_p(h_cnt.ptr)))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for kv in args.opt:
-        name, val = kv.split("=")
-        store.set_option(name, int(val))
-
-    # ---- timed region 1: device-resident queries -------------------------------------------------
-    store.set_option("profile", 0)
-    for _ in range(args.warmup):
-        step_device(q_dev)
-    store.set_option("profile", 1)
-    store.last_timings()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = lib.scn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device(q_dev)
-    e1.record()
-    barrier()
-    launches = lib.scn_launch_count() - launches0
-    clocks = sampler.stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    timings = store.last_timings()
-    counters = store.last_counters()
-    store.set_option("profile", 0)
-
-    # ---- timed region 2: end to end through the host-buffer call ---------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-
+    ms_total, timings, counters, launches, clocks = time_device(ctx, step_device, steps, warmup, store)
+    e2e_s = time_host(ctx, step_e2e, steps, max(1, warmup // 2))
+    block = None
     if rank == 0:
-        pk = peaks()
-        ms_step = ms_total / args.steps
-        nq_job = nq_total if kind == "hnsw" else nq   # replicas split the batch; shards share it
-        value = nq_job / (ms_step * 1e-3)
-        # dominant kernel + its roofline
-        roof = None
-        if timings:
-            top = max(timings.items(), key=lambda kv: kv[1][0])
-            name, (tot_ms, cnt) = top
-            avg_ms = tot_ms / max(cnt, 1)
-            share = tot_ms / max(sum(v[0] for v in timings.values()), 1e-9)
-            if name == "tensor_filter":
-                flops = 2.0 * nq * n_local * dim
-                ach = flops / (avg_ms * 1e-3) / 1e12
-                # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-                traffic = 2.387e9 if (rows, dim, nq, world) == (1_000_000, 768, 10_000, 1) else None
-                roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_sustained"], "traffic": traffic,
-                        "traffic_source": "profiles/r01_ncu_tensor_filter_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
-                        "algorithmic_flop": flops, "peak_source": pk["source"] + " (sustained bf16)",
-                        "launch_ms": avg_ms, "share_of_step": share}
-            elif name == "flat_exact_scan":
-                passes = (nq + 7) // 8
-                byts = float(passes) * n_local * (dim * 4 + (4 if metric == 2 else 0))
-                ach = byts / (avg_ms * 1e-3) / 1e9
-                roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["source"], "launch_ms": avg_ms,
-                        "share_of_step": share, "note": f"{passes} passes of 8 queries over fp32 rows per launch"}
-            elif name.startswith("hnsw_search") and counters:
-                evals, hops = counters[0], counters[1]
-                byts = evals * dim * 4.0 + hops * 32 * 4.0
-                ach = byts / (avg_ms * 1e-3) / 1e9
-                # DRAM bytes per launch from the committed ncu --set full capture of this exact workload: BELOW the
-                # algorithmic bytes, because the walks of a batch share hub rows and L2 serves them
-                traffic = 8.701e9 if (rows, dim, nq, world, args.ef) == (1_000_000, 128, 10_000, 1, 128) else None
-                roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": ach / pk["hbm"], "traffic": traffic,
-                        "traffic_source": "profiles/r01_ncu_hnsw_search_metrics.json (dram__bytes_read+write, bytes/launch)" if traffic else None,
-                        "algorithmic_bytes": byts, "peak_source": pk["source"], "launch_ms": avg_ms,
-                        "share_of_step": share, "note": f"{evals / nq:.0f} distance evals, {hops / nq:.0f} expansions per query (counted on device); "
-                                                        "algorithmic bytes = evals*dim*4 + expansions*2M*4"}
-        # CPU baseline on a bounded sample (rank 0, N = 1 only)
+        threads = ctx.threads
+        step_e2e()
+        gpu_ids = h_ids.array.copy()
+        # exact ground truth for recall@k: the GPU flat scan over the same store (itself oracle-checked in tests/)
+        gt_ids, _, _ = store.search_flat(hq.array[:nq], k)
+        # the oracle's walk of the same graph on a sample: ids must be identical (the kernels reproduce
+        # the reference's walk), so recall is identical by construction — and measured both ways
+        n_s = min(nq, 500)
+        o_ids, o_dist, o_cnt, _ = h.search_batch(hq.array[:n_s], k, ef, nthreads=threads)
+        same = bool(np.array_equal(gpu_ids[:n_s], o_ids) and np.array_equal(h_dist.array[:n_s], o_dist))
+        verified = {"queries": n_s, "identical": same,
+                    "against": "CPU oracle HNSW.Search over the same graph (ids and fp32 distance bits)",
+                    "recall_at_k_gpu": recall_at_k(gpu_ids[:n_s], gt_ids[:n_s]), "recall_at_k_oracle": recall_at_k(o_ids, gt_ids[:n_s]),
+                    "recall_at_k_gpu_all_queries": recall_at_k(gpu_ids[:nq], gt_ids)}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            if kind == "flat":
-                db_host = np.concatenate([store.get(np.arange(i, min(i + 65536, n_local), dtype=np.uint64) + 1)
-                                          for i in range(0, n_local, 65536)])
-                ns = min(nq, threads)
-                rounds = 16 if rows * dim >= 5e8 else 32   # about 10 s of host work at C2 (0.6 s per round)
-                qps, dt = cpu_flat_qps(db_host, q_host.numpy()[:ns], metric, k, threads, rounds)
-                cpu = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                       "sample": f"{ns * rounds} queries ({rounds} rounds x {ns}, one per thread) over the full database, {dt:.1f}s wall"}
-                del db_host
-            else:
-                # the whole batch, repeated until about 10 s of host work have been timed
-                ns, reps = nq, 0
-                t0 = time.perf_counter()
-                while reps < 64 and time.perf_counter() - t0 < 10.0:
-                    h.search_batch(q_host.numpy()[:ns], k, args.ef, nthreads=threads)
-                    reps += 1
-                dt = time.perf_counter() - t0
-                cpu = {"value": ns * reps / dt, "unit": "queries/s", "cores": threads, "kind": "port",
-                       "sample": f"{reps} x {ns} queries, ef={args.ef}, same graph, {dt:.1f}s wall; graph "
-                                 + (f"built in {build_s:.0f}s (1 thread)" if build_s else "loaded from bench_cache/")}
-        line = {
-            "metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16 filter + f32 exact rerank" if (timings and "tensor_filter" in timings) else "f32",
-            "data": "synthetic gaussian (torch.randn on device, seeded)",
-            "config": {"workload": f"{args.workload}: {rows}x{dim} {METRIC_NAME[metric]} {kind} k={k} nq={nq}"
-                                   + (f" ef={args.ef}" if kind == "hnsw" else ""),
-                       "rows": rows, "dim": dim, "metric": METRIC_NAME[metric], "nq": nq, "k": k,
-                       "sharding": f"rows/{world}" if kind == "flat" else f"replicas x{world}, query batch split",
-                       "shard_merge": {"p2p": "fused into the search epilogue over NVLink peer memory (P2P stores + flags)",
-                                       "nccl": "NCCL all_gather of keys and ids + merge kernel", "none": None}[merge_mode],
-                       "l2_policy": "database (>= 3 GB fp32 + bf16 mirror per pass) is far larger than the 126 MB L2; no flush needed"
-                       if rows * dim * 4 > 4e8 else "working set fits L2: flush not applied (small workload, not the headline)"},
-            "e2e": {"value": nq_job * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
-                    "d2h_bytes_per_step": nq * k * 12 + nq * 4, "timer": "host wall clock around the blocking C-ABI call"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "kernels_ms_per_step": {n_: v[0] / args.steps for n_, v in timings.items()},
-            "counters": counters,
+        if world == 1 and cpu_baseline:
+            reps, t0 = 0, time.perf_counter()
+            while reps < 64 and time.perf_counter() - t0 < 10.0:   # the whole batch, repeated for about 10 s of host work
+                h.search_batch(hq.array[:nq], k, ef, nthreads=threads)
+                reps += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": nq * reps / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                   "sample": f"{reps} x {nq} queries, ef={ef}, same graph, {dt:.1f}s wall; graph "
+                             + (f"built in {build_s:.0f}s (1 thread)" if build_s else "loaded from bench_cache/")}
+        ms_step = ms_total / steps
+        roof = roofline_of(ctx, timings, counters, clocks, rows=rows, n_local=rows, dim=dim, metric=metric, nq=nq, world=world, ef=ef)
+        sweep = []
+        for e in ef_sweep:
+            # queries/s at recall: one point per ef on the same graph (3 timed steps each; recall of the GPU on
+            # all queries, of the oracle on the sample; ef < k returns fewer than k results, as in the reference)
+            cur_ef[0] = e
+            for _ in range(2):
+                step_device()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step_device()
+            e1.record()
+            torch.cuda.synchronize()
+            step_e2e()
+            oi, _, _, _ = h.search_batch(hq.array[:n_s], k, e, nthreads=threads)
+            sweep.append({"ef": e, "value": nq * 3 / (e0.elapsed_time(e1) * 1e-3), "unit": "queries/s",
+                          "recall_at_k_gpu": recall_at_k(h_ids.array[:nq], gt_ids), "recall_at_k_oracle_sample": recall_at_k(oi, gt_ids[:n_s]),
+                          "identical_to_oracle_sample": bool(np.array_equal(h_ids.array[:n_s], oi))})
+        cur_ef[0] = ef
+        block = {
+            "workload": f"{name}: {rows}x{dim} {METRIC_NAME[metric]} hnsw k={k} nq={nq_total} ef={ef}",
+            "value": nq_total / (ms_step * 1e-3), "unit": "queries/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+            "dtype": "f32",
+            "config": {"workload": f"{name}: {rows}x{dim} {METRIC_NAME[metric]} hnsw k={k} nq={nq_total} ef={ef}", "rows": rows,
+                       "dim": dim, "metric": METRIC_NAME[metric], "nq": nq_total, "k": k, "ef": ef, "M": 16, "efConstruction": 200,
+                       "sharding": f"replicas x{world}, query batch split",
+                       "l2_policy": "1M x 128 fp32 rows + adjacency (0.64 GB) exceed the 126 MB L2; walks are random gathers"
+                       if rows * dim * 4 > 4e8 else "working set fits L2 (small workload, not the headline)",
+                       "operating_point": "the reference's plain closest-M neighbour selection (hnsw.go:560-583, no diversity "
+                                          "heuristic) on i.i.d. Gaussian data caps recall well below 1; GPU and oracle walks are "
+                                          "identical, so recall is the reference's own at every ef — see ef_sweep"},
+            "e2e": {"value": nq_total * steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                    "d2h_bytes_per_step": nq * (k * 12 + 4),
+                    "timer": "host wall clock around the blocking host-buffer C-ABI call (scn_search_hnsw), pinned buffers"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "verified": verified,
+            "ef_sweep": sweep, "kernels_ms_per_step": {n_: v[0] / steps for n_, v in timings.items()}, "counters": counters,
         }
+    ctx.barrier()
+    for b in (hq, h_ids, h_dist, h_cnt):
+        b.close()
+    store.close()
+    del q_dev, out_ids, out_dist, out_cnt, h, db_host
+    torch.cuda.empty_cache()
+    return block
+
+
+def run_ours(args, wl, name):
+    ctx = Ctx(args)
+    rows, dim, metric, nq, k, kind = wl
+    ef_sweep = [int(x) for x in args.ef_sweep.split(",") if x] if args.ef_sweep else []
+    if kind == "flat":
+        main = bench_flat(ctx, wl, name, args.steps, args.warmup, not args.no_cpu_baseline)
+    else:
+        main = bench_hnsw(ctx, wl, name, args.ef, args.steps, args.warmup, not args.no_cpu_baseline, ef_sweep)
+    secondary = []
+    if not args.no_secondary and name == "c2" and not (args.rows or args.dim or args.nq):
+        # the other BASELINE.json configurations, measured in the same run so that they are on the driver's record
+        if ctx.world == 1 and os.path.exists(graph_cache_path(*WORKLOADS["c3"][:3])):
+            secondary.append(bench_hnsw(ctx, WORKLOADS["c3"], "c3", 128, args.steps, args.warmup, not args.no_cpu_baseline,
+                                        [16, 32, 64, 256, 512]))
+        elif ctx.world == 1 and ctx.rank == 0:
+            secondary.append({"workload": "c3", "skipped": "bench_cache/ holds no reference-built 1M x 128 graph on this box "
+                                                           "(the serial reference construction takes hours; see DESIGN.md)"})
+        if ctx.world >= 2:
+            secondary.append(bench_flat(ctx, WORKLOADS["c4"], "c4", max(2, min(args.steps, 5)), 3, False))
+    if ctx.rank == 0:
+        line = {
+            "metric": "queries/sec", "value": main["value"], "unit": "queries/s", "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": main["dtype"],
+            "data": "synthetic gaussian (torch.randn on device, seeded; the oracle checks read the same rows back from the GPU)"
+            if kind == "flat" else "synthetic gaussian (numpy, seeded)",
+            "config": main["config"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+            "roofline": main["roofline"], "cpu_baseline": main["cpu_baseline"], "verified": main["verified"],
+            "kernels_ms_per_step": main["kernels_ms_per_step"], "counters": main["counters"],
+        }
+        if "ef_sweep" in main:
+            line["ef_sweep"] = main["ef_sweep"]
+        if secondary:
+            line["secondary"] = [s for s in secondary if s]
         emit(line)
-    if exchange is not None:
-        exchange.status(torch.cuda.current_stream().cuda_stream)   # a missed peer arrival would have invalidated the run
-        barrier()
-        exchange.close()
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 _JSON_OUT = None
@@ -519,11 +780,15 @@ def main():
     ap.add_argument("--rows", type=int)
     ap.add_argument("--dim", type=int)
     ap.add_argument("--nq", type=int)
+    ap.add_argument("--metric", type=int, choices=[1, 2, 3])
     ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--ef-sweep", default="", help="HNSW workloads: comma-separated ef values measured after the main point")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default c2 run: skip the C3 (N = 1) / C4 (N >= 2) blocks")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (scn_set_option), repeatable")
     ap.add_argument("--merge", default="p2p", choices=["p2p", "nccl"], help="row-shard exchange for --gpus > 1")
     args = ap.parse_args()
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     wl = list(WORKLOADS[args.workload])
     if args.rows:
         wl[0] = args.rows
@@ -531,12 +796,14 @@ def main():
         wl[1] = args.dim
     if args.nq:
         wl[3] = args.nq
+    if args.metric:
+        wl[2] = args.metric
     if args.workload == "c1" and args.ef == 128:
         args.ef = 100
     if args.impl == "reference":
         run_reference(args, tuple(wl))
     else:
-        run_ours(args, tuple(wl))
+        run_ours(args, tuple(wl), args.workload)
 
 
 if __name__ == "__main__":

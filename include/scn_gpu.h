@@ -18,7 +18,8 @@
  *   HNSW.Search rerank step on caller-chosen candidates    scn_rerank                 (hnsw.go:317-347)
  *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
  *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
- *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev, scn_search_flat_exchange_dev
+ *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev, scn_search_flat_exchange[_dev]
+ *   VectorIndex.Search over a collection sharded over G GPUs scn_shards_search_flat     (interfaces.go:87-111)
  *   RDBManager.Load + RestoreFromSnapshot + ImportGraph    scn_store_load_rdb         (rdb.go:179-237, database.go:398-493)
  *   Collection.Compact (drop deleted, rebuild)             scn_store_compact          (collection.go:283-313)
  *   Collection.Search called by many goroutines            scn_batcher_search         (collection.go:193-204)
@@ -92,6 +93,12 @@ SCN_API const char* scn_last_error(void);
 /* Number of kernels launched by this library in this process so far (all threads). */
 SCN_API uint64_t scn_launch_count(void);
 
+/* Pinned (page-locked) host memory for query / result buffers. The host-buffer entry points accept
+ * any host pointer: pinned buffers are DMA-ed directly, pageable ones (a Go slice) go through the
+ * library's own pinned staging chunks, which costs one extra memcpy. */
+SCN_API int32_t scn_host_alloc(uint64_t bytes, void** out);
+SCN_API int32_t scn_host_free(void* p);
+
 /* ---- device vector store ------------------------------------------------------------------ */
 
 /* metric must be 1, 2 or 3 (else SCN_ERR_INVALID_PARAMETERS, like NewDistanceCalculator). */
@@ -110,6 +117,10 @@ SCN_API int32_t scn_store_append_dev(scn_store* s, const float* d_vecs, const ui
 
 /* Soft delete (HNSW.Delete). Unknown id -> SCN_ERR_VECTOR_NOT_FOUND; already deleted is a no-op. */
 SCN_API int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n);
+/* Restore form (ImportGraphState, hnsw.go:749-804): sets the soft-delete flags of a snapshot and
+ * leaves entrypoint / maxLayer exactly as uploaded (hnsw.go:791-793) — a snapshot whose entry point
+ * is flagged deleted then answers every search with no result, like the reference. */
+SCN_API int32_t scn_store_restore_deleted(scn_store* s, const uint64_t* ids, uint64_t n);
 
 /* Collection.Compact (collection.go:283-313): physically removes the soft-deleted rows. Surviving
  * rows keep their insertion order and ids; the graph is dropped (the reference rebuilds the index
@@ -210,26 +221,60 @@ SCN_API int32_t scn_search_flat_shard_dev(scn_store* s, const float* d_q, uint64
 SCN_API int32_t scn_merge_topk_dev(int32_t device, const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq,
                            uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
 
-/* ---- row-sharded search with the shard exchange fused over NVLink peer memory -------------------
- * One scn_exchange per rank (= per GPU / row shard). The epilogue of the shard-local search stores
- * its top-k (key, id) lists straight into every rank's exchange buffer (P2P stores) and raises a
- * flag there; each rank then merges from its own memory. Replaces the all_gather + merge of the
- * NCCL formulation; results are bit-identical to the single-GPU search. Every rank must call
- * scn_search_flat_exchange_dev for the same batch (same nq), like a collective.
+/* ---- row-sharded search with both exchanges fused over NVLink peer memory ------------------------
+ * One scn_exchange per rank (= per GPU / row shard). A batch of nq queries is cut into `world`
+ * contiguous slices (scn_exchange_slice); rank r answers slice r. Per call every rank (1) gathers the
+ * batch over NVLink from the slices each rank holds (optional), (2) scans its rows for the whole
+ * batch, (3) stores each top-k (key, id) list into the buffer of the rank that owns the query
+ * (16-byte P2P stores) and raises a flag there, (4) merges its own slice from local memory. Replaces
+ * H2D of the whole batch on every rank + all_gather + merge of the NCCL formulation; results are
+ * bit-identical to the single-GPU search. Every rank must call for the same batch (same nq), like a
+ * collective; ranks driven from one process must use different streams or devices.
  *   between processes : exchange the 64-byte handles (any transport), then scn_exchange_connect
- *   inside one process: scn_exchange_connect_local with the peers' objects */
+ *   inside one process: scn_exchange_connect_local with the peers' objects (or use scn_shards_*)
+ * dim = query dimension for the NVLink query gather (0: not used, q_is_slice must be 0). */
 #define SCN_IPC_HANDLE_BYTES 64
 typedef struct scn_exchange scn_exchange;
-SCN_API int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint64_t max_nq, uint32_t k, scn_exchange** out);
+SCN_API int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint64_t max_nq, uint32_t k, uint32_t dim,
+                            scn_exchange** out);
 SCN_API int32_t scn_exchange_local_handle(scn_exchange* ex, void* out_handle);
 SCN_API int32_t scn_exchange_connect(scn_exchange* ex, const void* handles /* [world][64] */);
 SCN_API int32_t scn_exchange_connect_local(scn_exchange* ex, scn_exchange* const* peers /* [world] */);
 SCN_API int32_t scn_exchange_destroy(scn_exchange* ex);
-SCN_API int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, uint64_t nq, uint32_t k,
-                                     uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
-                                     void* stream);
-/* Synchronises `stream`; SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out. */
+/* Slice of a batch of nq queries that `rank` answers: queries [first, first + count). */
+SCN_API int32_t scn_exchange_slice(const scn_exchange* ex, uint64_t nq, uint32_t rank, uint64_t* out_first, uint64_t* out_count);
+/* d_q: the whole batch [nq][dim] (q_is_slice = 0) or this rank's slice only (q_is_slice = 1). The
+ * outputs hold the results of this rank's slice: [count][k]. */
+SCN_API int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, int32_t q_is_slice, uint64_t nq,
+                                     uint32_t k, uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist,
+                                     uint32_t* d_out_counts, void* stream);
+/* Host-buffer, blocking form of one rank's call: q_slice = this rank's slice of the batch, outputs =
+ * the results of that slice. SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out. */
+SCN_API int32_t scn_search_flat_exchange(scn_store* s, scn_exchange* ex, const float* q_slice, uint64_t nq, uint32_t k,
+                                 uint64_t row_base, uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
+/* Synchronises `stream`; SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out since the
+ * previous status call (the results of such a call are empty). Clears the condition. */
 SCN_API int32_t scn_exchange_status(scn_exchange* ex, void* stream);
+
+/* ---- one collection row-sharded over the GPUs of one box (single process) -----------------------
+ * The multi-device form of the boundary: core.VectorIndex.Search (interfaces.go:87-111) stays ONE
+ * blocking host-buffer call and drives all G GPUs (one worker thread per device inside the library,
+ * the fused exchange above between them). Shard g owns the global rows [g*per, (g+1)*per),
+ * per = ceil(capacity_rows / G), filled in insertion order; rows beyond the declared capacity go to
+ * the last shard. ids == NULL assigns global row + 1 (collection.go:57,115-116). Results are
+ * bit-identical to scn_search_flat of one store holding all rows. */
+typedef struct scn_shards scn_shards;
+SCN_API int32_t scn_shards_create(const int32_t* devices, int32_t ndev, uint32_t dim, int32_t metric, uint64_t capacity_rows,
+                          scn_shards** out);
+SCN_API int32_t scn_shards_destroy(scn_shards* sh);
+SCN_API int32_t scn_shards_count(scn_shards* sh);
+SCN_API scn_store* scn_shards_store(scn_shards* sh, int32_t i);   /* shard i (options, statistics); owned by sh */
+SCN_API int32_t scn_shards_append(scn_shards* sh, const float* vecs, const uint64_t* ids, uint64_t n);
+SCN_API int32_t scn_shards_mark_deleted(scn_shards* sh, const uint64_t* ids, uint64_t n);
+SCN_API int32_t scn_shards_stats(scn_shards* sh, scn_stats* out);   /* summed over the shards; device = -1 */
+SCN_API int32_t scn_shards_set_option(scn_shards* sh, const char* name, int64_t value);
+SCN_API int32_t scn_shards_search_flat(scn_shards* sh, const float* q, uint64_t nq, uint32_t k, uint64_t* out_ids, float* out_dist,
+                               uint32_t* out_counts);
 
 /* ---- micro-batching of single-query calls ------------------------------------
  * The reference's API is one query per call (Collection.Search, collection.go:193-204; HNSW.Search,
@@ -260,7 +305,9 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *                       stages of 512 B / 2 x 512 B / 256 B; "hnsw_gather_long" the auto choice for rows > 512 B
  *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory
  *   "hnsw_hash"         entries of the visited table (0 = auto); "hnsw_per_sm" cap on resident queries per SM
- *   "hnsw_early"        1 = rows requested before the visited test (default); "hnsw_rank" 1 = MATCH.ANY slot ranking
+ *   "hnsw_early"        1 = rows requested before the visited test (default)
+ *   "auto_id_base"      (empty store only) auto-assigned ids become value + row + 1: a row shard of a larger
+ *                       collection numbers its rows globally
  *   "profile"           1 = record per-kernel CUDA-event timings and the device counters */
 SCN_API int32_t scn_set_option(scn_store* s, const char* name, int64_t value);
 /* Per-kernel CUDA-event timings accumulated since the previous call (option "profile" = 1):

@@ -3,10 +3,10 @@ own index/distance interfaces. The product is `libscn_gpu.so` (CUDA, C ABI in in
 this package is the tested host-side mirror of the Go cgo shim in go/."""
 from .types import (DistanceMetric, ErrorCode, GraphState, HNSWParams, ScintireteError, SearchParams, SearchResult,
                     Vector)
-from .index import (Batcher, DeviceStore, DistanceCalculator, GPUFlatIndex, GPUHNSWIndex, IndexFactory, batch_distance,
+from .index import (Batcher, DeviceStore, PinnedBuffer, DistanceCalculator, GPUFlatIndex, GPUHNSWIndex, IndexFactory, batch_distance,
                     dot_product, new_distance_calculator, normalize_vector, vector_magnitude)
 
 __all__ = ["DistanceMetric", "ErrorCode", "GraphState", "HNSWParams", "ScintireteError", "SearchParams",
-           "SearchResult", "Vector", "Batcher", "DeviceStore", "DistanceCalculator", "GPUFlatIndex", "GPUHNSWIndex",
+           "SearchResult", "Vector", "Batcher", "DeviceStore", "PinnedBuffer", "DistanceCalculator", "GPUFlatIndex", "GPUHNSWIndex",
            "IndexFactory", "batch_distance", "dot_product", "new_distance_calculator", "normalize_vector",
            "vector_magnitude"]

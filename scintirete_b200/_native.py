@@ -33,6 +33,8 @@ class RdbInfo(C.Structure):
 SIGNATURES = {
     "scn_last_error": (C.c_char_p, []),
     "scn_launch_count": (C.c_uint64, []),
+    "scn_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "scn_host_free": (C.c_int32, [C.c_void_p]),
     "scn_store_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p)]),
     "scn_store_destroy": (C.c_int32, [C.c_void_p]),
     "scn_store_reserve": (C.c_int32, [C.c_void_p, C.c_uint64]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "scn_store_append": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "scn_store_append_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "scn_store_mark_deleted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_store_restore_deleted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "scn_store_compact": (C.c_int32, [C.c_void_p, u64p]),
     "scn_store_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
     "scn_store_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -63,13 +66,27 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "scn_store_load_rdb": (C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p),
                                         C.POINTER(RdbInfo)]),
-    "scn_exchange_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "scn_exchange_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_void_p)]),
+    "scn_exchange_slice": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint32, u64p, u64p]),
+    "scn_search_flat_exchange": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_shards_create": (C.c_int32, [i32p, C.c_int32, C.c_uint32, C.c_int32, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "scn_shards_destroy": (C.c_int32, [C.c_void_p]),
+    "scn_shards_count": (C.c_int32, [C.c_void_p]),
+    "scn_shards_store": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "scn_shards_append": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_shards_mark_deleted": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "scn_shards_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
+    "scn_shards_set_option": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "scn_shards_search_flat": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "scn_exchange_local_handle": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "scn_exchange_connect": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "scn_exchange_connect_local": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "scn_exchange_destroy": (C.c_int32, [C.c_void_p]),
-    "scn_search_flat_exchange_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64,
-                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scn_search_flat_exchange_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32,
+                                                  C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scn_exchange_status": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "scn_batcher_create": (C.c_int32, [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "scn_batcher_destroy": (C.c_int32, [C.c_void_p]),

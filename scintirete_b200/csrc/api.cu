@@ -83,7 +83,7 @@ int32_t scn_search_flat(scn_store* s, const float* q, uint64_t nq, uint32_t k, u
   SCN_TRY(scratch.alloc(&d_ids, nq * k));
   SCN_TRY(scratch.alloc(&d_dist, nq * k));
   SCN_TRY(scratch.alloc(&d_counts, nq));
-  SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCN_TRY(copy_to_device(d_q, q, nq * s->dim * sizeof(float), st));
   SCN_TRY(scn_search_flat_dev(s, d_q, nq, k, d_ids, d_dist, d_counts, st));
   SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -129,7 +129,7 @@ int32_t scn_search_hnsw(scn_store* s, const float* q, uint64_t nq, uint32_t k, u
   SCN_TRY(scratch.alloc(&d_ids, nq * k));
   SCN_TRY(scratch.alloc(&d_dist, nq * k));
   SCN_TRY(scratch.alloc(&d_counts, nq));
-  SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCN_TRY(copy_to_device(d_q, q, nq * s->dim * sizeof(float), st));
   SCN_TRY(scn_search_hnsw_dev(s, d_q, nq, k, ef, d_ids, d_dist, d_counts, st));
   SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -164,7 +164,7 @@ int32_t scn_rerank(scn_store* s, const float* q, uint64_t nq, const uint64_t* ca
   SCN_TRY(scratch.alloc(&d_ids, nq * k));
   SCN_TRY(scratch.alloc(&d_dist, nq * k));
   SCN_TRY(scratch.alloc(&d_counts, nq));
-  SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCN_TRY(copy_to_device(d_q, q, nq * s->dim * sizeof(float), st));
   SCN_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   SCN_TRY(rerank_rows(s, d_q, nq, d_rows, ncand, k, 0, d_keys, st));
   SCN_TRY(keys_to_results(s, d_keys, nq, 0, d_ids, d_dist, d_counts, k, st));
@@ -231,7 +231,7 @@ int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t nq, float
   float *d_q = nullptr, *d_o = nullptr;
   SCN_TRY(scratch.alloc(&d_q, nq * s->dim));
   SCN_TRY(scratch.alloc(&d_o, nq * s->rows));
-  SCN_CUDA(cudaMemcpyAsync(d_q, q, nq * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  SCN_TRY(copy_to_device(d_q, q, nq * s->dim * sizeof(float), st));
   SCN_TRY(tensor_debug_scores(s, d_q, nq, d_o, st));
   SCN_CUDA(cudaMemcpyAsync(out_scores, d_o, nq * s->rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaStreamSynchronize(st));

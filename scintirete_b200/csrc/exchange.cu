@@ -1,18 +1,34 @@
-// exchange.cu — row-sharded exact search with the per-shard top-k exchange fused into the search's
-// own epilogue over NVLink peer memory ("optional fusion").
+// exchange.cu — row-sharded exact search with both of its exchanges fused over NVLink peer memory
+// ("optional fusion").
 //
-// The NCCL formulation is: shard-local search -> keys_to_results -> all_gather(keys) ->
-// all_gather(ids) -> merge_topk: three extra launches and two collectives for 16 B x nq x k per
-// rank (1.6 MB at 10 000 x 10) — pure latency. Here every rank owns one exchange buffer
-// [2 parities][world][max_nq*k] of (key, id) lists plus one arrival flag per (parity, peer), mapped
-// into every other rank (cudaIpc between processes, cudaDeviceEnablePeerAccess inside one process —
-// the reference server is ONE process, so that is the drop-in's natural form). The epilogue kernel
-// of the shard-local search converts its keys to ids and stores both lists straight into all
-// world buffers (plain 16-byte NVLink P2P stores), then the last block publishes the flags with a
-// system-scope release. A one-warp wait kernel acquires the world flags (with a time-out that is
-// reported, never a hang) and the ordinary merge kernel reads only local memory. Parity double
-// buffering is enough: a rank can start call e+2 only after its merge of call e+1 saw every peer's
-// flag e+1, which each peer sets after its own merge of call e.
+// The NCCL formulation of one sharded batch is: H2D of the whole query batch on every rank ->
+// shard-local search -> keys_to_results -> all_gather(keys) -> all_gather(ids) -> merge_topk on
+// every rank. Here every rank owns one exchange buffer, mapped into every other rank (cudaIpc
+// between processes, cudaDeviceEnablePeerAccess inside one process — the reference server is ONE
+// process, so that is the drop-in's natural form):
+//
+//   flags      u32 [2 kinds][2 parities][16 peers]          arrival flags (value = call epoch, never 0)
+//   lists      u64 keys [2 parities][world][slice_cap * k]  + ids, same shape
+//   queries    f32 [2 parities][max_nq * dim]               the assembled query batch (dim > 0 only)
+//
+// and a batch of nq queries is cut into `world` contiguous slices (slice r = queries
+// [r*per, min(nq, (r+1)*per)), per = ceil(nq / world)); rank r answers slice r:
+//
+//   1. query gather (optional): each rank copies only ITS slice from the host (1/world of the PCIe
+//      traffic) and a kernel stores it into every rank's query buffer with 16-byte P2P stores, then
+//      raises the query flags; a one-warp kernel waits for the world flags of the call.
+//   2. shard-local search of the WHOLE batch over the local rows -> sorted (key, row) lists.
+//   3. push: every list element goes to exactly one peer — the owner of its query's slice — as a
+//      (key, id) pair, 16-byte P2P stores; the last block raises the list flags (st.release.sys).
+//   4. wait for the world list flags (time-out reported through a status word, never a hang), then
+//      merge_topk over the rank's own slice from LOCAL memory. A timed-out call yields empty results.
+//
+// Keys carry global rows, so the merged slices are bit-identical to the single-GPU search. Parity
+// double buffering is enough: a rank can start call e+2 (which overwrites parity(e) buffers of its
+// peers) only after its own wait of call e+1 saw every peer's list flag e+1, which a peer raises
+// after its search e+1, i.e. after it finished reading parity(e) (its merge and its search of call
+// e precede it in stream order). Ranks driven inside one process must use different streams (or
+// devices): a rank's wait spins until the other ranks' pushes have run.
 #include <cstring>
 
 #include "store.h"
@@ -21,53 +37,52 @@ using namespace scn;
 
 struct scn_exchange {
   int32_t device = 0;
-  uint32_t rank = 0, world = 1, k = 0;
+  uint32_t rank = 0, world = 1, k = 0, dim = 0;
   uint64_t max_nq = 0;
+  uint64_t slice_cap = 0;                    // queries per slice the list buffers can hold
   uint64_t epoch = 0;
   unsigned char* local = nullptr;            // this rank's buffer
   unsigned char* peer[16] = {};              // peer[r] = rank r's buffer as seen from here (peer[rank] = local)
   bool opened_ipc[16] = {};
   bool connected = false;
-  uint32_t* d_done = nullptr;                // block completion counter of the push kernel
-  uint32_t* d_status = nullptr;              // 0 ok, 1 = wait timed out
+  uint32_t* d_done = nullptr;                // [0] push blocks done, [1] scatter blocks done, [2] status
+  uint32_t* d_status = nullptr;              // 0 ok, 1 = a wait timed out since the last status read
   size_t bytes = 0;
 };
 
 namespace {
 
-constexpr size_t FLAG_BYTES = 4096;  // [2][16] u32 flags, padded
+constexpr size_t FLAG_BYTES = 4096;  // [2 kinds][2 parities][16] u32 flags, padded
+enum : uint32_t { FLAG_LISTS = 0, FLAG_QUERIES = 1 };
 
-__host__ __device__ inline size_t list_elems(uint64_t max_nq, uint32_t k) { return (size_t)max_nq * k; }
-// layout: flags | keys[2][world][max_nq*k] | ids[2][world][max_nq*k]
-__host__ __device__ inline uint32_t* flags_of(unsigned char* base) { return reinterpret_cast<uint32_t*>(base); }
-__host__ __device__ inline uint64_t* keys_of(unsigned char* base, uint32_t parity, uint32_t world, uint32_t shard, size_t le) {
-  return reinterpret_cast<uint64_t*>(base + FLAG_BYTES) + ((size_t)parity * world + shard) * le;
+struct Layout {
+  uint32_t world;
+  size_t le;        // list elements per (parity, shard): slice_cap * k
+  size_t q_floats;  // floats per query buffer: max_nq * dim
+};
+
+__host__ __device__ inline uint32_t* flag_of(unsigned char* base, uint32_t kind, uint32_t parity, uint32_t r) {
+  return reinterpret_cast<uint32_t*>(base) + (kind * 2 + parity) * 16 + r;
 }
-__host__ __device__ inline uint64_t* ids_of(unsigned char* base, uint32_t parity, uint32_t world, uint32_t shard, size_t le) {
-  return reinterpret_cast<uint64_t*>(base + FLAG_BYTES) + ((size_t)2 * world + (size_t)parity * world + shard) * le;
+__host__ __device__ inline uint64_t* keys_of(unsigned char* base, const Layout& L, uint32_t parity, uint32_t shard) {
+  return reinterpret_cast<uint64_t*>(base + FLAG_BYTES) + ((size_t)parity * L.world + shard) * L.le;
+}
+__host__ __device__ inline uint64_t* ids_of(unsigned char* base, const Layout& L, uint32_t parity, uint32_t shard) {
+  return reinterpret_cast<uint64_t*>(base + FLAG_BYTES) + ((size_t)2 * L.world + (size_t)parity * L.world + shard) * L.le;
+}
+__host__ __device__ inline float* queries_of(unsigned char* base, const Layout& L, uint32_t parity) {
+  return reinterpret_cast<float*>(base + FLAG_BYTES + (size_t)4 * L.world * L.le * sizeof(uint64_t)) + (size_t)parity * L.q_floats;
 }
 
-struct PushArgs {
+struct PeerArgs {
   unsigned char* peer[16];
-  const uint64_t* keys;   // [nq*k] shard-local sorted keys (global rows)
-  const uint64_t* row_ids;
-  uint32_t world, rank, parity, epoch;
-  uint64_t n;             // nq*k
-  uint64_t row_base;
-  size_t le;
+  Layout L;
+  uint32_t rank, parity, epoch;
   uint32_t* done;
 };
 
-// keys -> ids, then both lists into every rank's buffer; the last block raises the flags
-__global__ void __launch_bounds__(256) push_results_kernel(PushArgs a) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t key = a.keys[i];
-    const uint64_t id = (key == KEY_NONE) ? 0ull : a.row_ids[(uint32_t)key - (uint32_t)a.row_base];
-    for (uint32_t p = 0; p < a.world; ++p) {
-      keys_of(a.peer[p], a.parity, a.world, a.rank, a.le)[i] = key;
-      ids_of(a.peer[p], a.parity, a.world, a.rank, a.le)[i] = id;
-    }
-  }
+// the last block of a grid raises this rank's flag of `kind` on every peer
+__device__ __forceinline__ void publish(const PeerArgs& a, uint32_t kind) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -75,20 +90,72 @@ __global__ void __launch_bounds__(256) push_results_kernel(PushArgs a) {
     if (prev == gridDim.x - 1) {
       *a.done = 0;
       __threadfence_system();
-      for (uint32_t p = 0; p < a.world; ++p) {
-        uint32_t* f = flags_of(a.peer[p]) + a.parity * 16 + a.rank;
+      for (uint32_t p = 0; p < a.L.world; ++p) {
+        uint32_t* f = flag_of(a.peer[p], kind, a.parity, a.rank);
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.epoch) : "memory");
       }
     }
   }
 }
 
+// Step 3. keys -> ids, then every (key, id) pair to the owner of its query's slice. With an even k
+// a thread moves two consecutive elements of one query with one 16-byte store per list.
+__global__ void __launch_bounds__(256) push_results_kernel(PeerArgs a, const uint64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ row_ids, uint64_t n /* nq*k */,
+                                                           uint32_t k, uint32_t per /* queries per slice */, uint32_t row_base) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  if ((k & 1u) == 0) {
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride * 2) {
+      const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(keys + i);
+      ulonglong2 id;
+      id.x = (kk.x == KEY_NONE) ? 0ull : row_ids[(uint32_t)kk.x - row_base];
+      id.y = (kk.y == KEY_NONE) ? 0ull : row_ids[(uint32_t)kk.y - row_base];
+      const uint32_t q = (uint32_t)(i / k);
+      const uint32_t p = q / per;
+      const size_t dst = i - (size_t)p * per * k;  // even: k is
+      *reinterpret_cast<ulonglong2*>(keys_of(a.peer[p], a.L, a.parity, a.rank) + dst) = kk;
+      *reinterpret_cast<ulonglong2*>(ids_of(a.peer[p], a.L, a.parity, a.rank) + dst) = id;
+    }
+  } else {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const uint64_t key = keys[i];
+      const uint64_t id = (key == KEY_NONE) ? 0ull : row_ids[(uint32_t)key - row_base];
+      const uint32_t q = (uint32_t)(i / k);
+      const uint32_t p = q / per;
+      const size_t dst = i - (size_t)p * per * k;
+      keys_of(a.peer[p], a.L, a.parity, a.rank)[dst] = key;
+      ids_of(a.peer[p], a.L, a.parity, a.rank)[dst] = id;
+    }
+  }
+  publish(a, FLAG_LISTS);
+}
+
+// Step 1. this rank's query slice -> every rank's query buffer (16-byte stores when aligned)
+__global__ void __launch_bounds__(256) scatter_queries_kernel(PeerArgs a, const float* __restrict__ src, uint64_t n_floats,
+                                                              uint64_t dst_off /* floats */) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((n_floats | dst_off) & 3ull) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  if (vec) {
+    for (uint64_t i = t0; i < n_floats / 4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      for (uint32_t p = 0; p < a.L.world; ++p) reinterpret_cast<float4*>(queries_of(a.peer[p], a.L, a.parity) + dst_off)[i] = v;
+    }
+  } else {
+    for (uint64_t i = t0; i < n_floats; i += stride) {
+      const float v = __ldg(src + i);
+      for (uint32_t p = 0; p < a.L.world; ++p) queries_of(a.peer[p], a.L, a.parity)[dst_off + i] = v;
+    }
+  }
+  publish(a, FLAG_QUERIES);
+}
+
 // one warp: lane r waits for rank r's flag of this call
-__global__ void wait_flags_kernel(const uint32_t* flags, uint32_t world, uint32_t parity, uint32_t epoch, uint32_t* status,
-                                  unsigned long long timeout_ns) {
+__global__ void wait_flags_kernel(const uint32_t* flags /* [16] of the kind and parity */, uint32_t world, uint32_t epoch,
+                                  uint32_t* status, unsigned long long timeout_ns) {
   const uint32_t r = threadIdx.x;
   if (r >= world) return;
-  const uint32_t* f = flags + parity * 16 + r;
+  const uint32_t* f = flags + r;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
@@ -105,11 +172,16 @@ __global__ void wait_flags_kernel(const uint32_t* flags, uint32_t world, uint32_
   }
 }
 
+constexpr unsigned long long WAIT_TIMEOUT_NS = 5000000000ull;
+
+uint32_t epoch_value(uint64_t epoch) { return (uint32_t)(epoch % 0xFFFFFFFFull) + 1u; }  // never 0, the flags' initial value
+
 }  // namespace
 
 extern "C" {
 
-int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint64_t max_nq, uint32_t k, scn_exchange** out) {
+int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint64_t max_nq, uint32_t k, uint32_t dim,
+                            scn_exchange** out) {
   if (!out) return fail(SCN_ERR_INVALID_PARAMETERS, "out is NULL");
   *out = nullptr;
   if (world == 0 || world > 16 || rank >= world) return fail(SCN_ERR_INVALID_PARAMETERS, "world must be in [1, 16] and rank < world");
@@ -120,19 +192,22 @@ int32_t scn_exchange_create(int32_t device, uint32_t rank, uint32_t world, uint6
   ex->rank = rank;
   ex->world = world;
   ex->k = k;
+  ex->dim = dim;
   ex->max_nq = max_nq;
-  ex->bytes = FLAG_BYTES + (size_t)4 * world * list_elems(max_nq, k) * sizeof(uint64_t);
+  ex->slice_cap = (max_nq + world - 1) / world;
+  const size_t le = (size_t)ex->slice_cap * k;
+  ex->bytes = FLAG_BYTES + (size_t)4 * world * le * sizeof(uint64_t) + (size_t)2 * max_nq * dim * sizeof(float);
   cudaError_t e = cudaMalloc(&ex->local, ex->bytes);  // cudaMalloc (not the async pool): IPC-exportable
   if (e == cudaSuccess) e = cudaMemset(ex->local, 0, FLAG_BYTES);
-  if (e == cudaSuccess) e = cudaMalloc(&ex->d_done, 2 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemset(ex->d_done, 0, 2 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&ex->d_done, 4 * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(ex->d_done, 0, 4 * sizeof(uint32_t));
   if (e != cudaSuccess) {
     cudaFree(ex->local);
     cudaFree(ex->d_done);
     delete ex;
     return cuda_fail(e, "exchange buffer allocation", __FILE__, __LINE__);
   }
-  ex->d_status = ex->d_done + 1;
+  ex->d_status = ex->d_done + 2;
   ex->peer[rank] = ex->local;
   ex->connected = (world == 1);
   *out = ex;
@@ -172,7 +247,8 @@ int32_t scn_exchange_connect_local(scn_exchange* ex, scn_exchange* const* peers)
   DeviceGuard g(ex->device);
   for (uint32_t r = 0; r < ex->world; ++r) {
     if (r == ex->rank) continue;
-    if (!peers[r] || peers[r]->world != ex->world || peers[r]->rank != r || peers[r]->max_nq != ex->max_nq || peers[r]->k != ex->k)
+    if (!peers[r] || peers[r]->world != ex->world || peers[r]->rank != r || peers[r]->max_nq != ex->max_nq || peers[r]->k != ex->k ||
+        peers[r]->dim != ex->dim)
       return fail(SCN_ERR_INVALID_PARAMETERS, "peer %u does not match this exchange", r);
     if (peers[r]->device != ex->device) {
       int can = 0;
@@ -200,60 +276,130 @@ int32_t scn_exchange_destroy(scn_exchange* ex) {
   return SCN_OK;
 }
 
-int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
-                                     uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
+int32_t scn_exchange_slice(const scn_exchange* ex, uint64_t nq, uint32_t rank, uint64_t* out_first, uint64_t* out_count) {
+  if (!ex || rank >= ex->world) return fail(SCN_ERR_INVALID_PARAMETERS, "bad exchange or rank");
+  const uint64_t per = (nq + ex->world - 1) / ex->world;
+  const uint64_t lo = std::min<uint64_t>(nq, (uint64_t)rank * per);
+  if (out_first) *out_first = lo;
+  if (out_count) *out_count = std::min<uint64_t>(nq, lo + per) - lo;
+  return SCN_OK;
+}
+
+int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, int32_t q_is_slice, uint64_t nq, uint32_t k,
+                                     uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                                     void* stream) {
   if (!s || !ex) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
   if (!ex->connected) return fail(SCN_ERR_INVALID_PARAMETERS, "exchange is not connected to its peers");
   if (s->device != ex->device) return fail(SCN_ERR_INVALID_PARAMETERS, "store and exchange live on different devices");
   if (k != ex->k || nq == 0 || nq > ex->max_nq) return fail(SCN_ERR_INVALID_PARAMETERS, "nq must be in [1, %llu] and k == %u", (unsigned long long)ex->max_nq, ex->k);
-  if (!d_q || !d_out_ids || !d_out_dist) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  if (q_is_slice && ex->dim != s->dim) return fail(SCN_ERR_INVALID_PARAMETERS, "the exchange was created for dim %u, the store has %u", ex->dim, s->dim);
+  if (row_base + s->rows >= (uint64_t)ROW_NONE) return fail(SCN_ERR_INVALID_PARAMETERS, "global row index exceeds 32 bits");
   DeviceGuard g(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  uint64_t q_lo = 0, q_n = 0;
+  scn_exchange_slice(ex, nq, ex->rank, &q_lo, &q_n);
+  if ((q_n && !d_q && q_is_slice) || (!q_is_slice && !d_q)) return fail(SCN_ERR_INVALID_PARAMETERS, "query pointer is NULL");
+  if (q_n && (!d_out_ids || !d_out_dist)) return fail(SCN_ERR_INVALID_PARAMETERS, "output pointer is NULL");
   Profiler prof(s, st);
   Scratch scratch(st);
-  uint64_t* d_keys = nullptr;
-  SCN_TRY(scratch.alloc(&d_keys, nq * k));
-  SCN_TRY(flat_keys(s, d_q, nq, k, row_base, d_keys, st, &prof));
   const uint64_t epoch = ++ex->epoch;
-  PushArgs a;
+  PeerArgs a;
   for (int r = 0; r < 16; ++r) a.peer[r] = ex->peer[r];
-  a.keys = d_keys;
-  a.row_ids = s->d_ids;
-  a.world = ex->world;
+  a.L.world = ex->world;
+  a.L.le = (size_t)ex->slice_cap * k;
+  a.L.q_floats = (size_t)ex->max_nq * ex->dim;
   a.rank = ex->rank;
   a.parity = (uint32_t)(epoch & 1);
-  a.epoch = (uint32_t)epoch;
-  a.n = nq * k;
-  a.row_base = row_base;
-  a.le = list_elems(ex->max_nq, k);
+  a.epoch = epoch_value(epoch);
+  const uint32_t per = (uint32_t)((nq + ex->world - 1) / ex->world);
+
+  // ---- 1. query gather over NVLink --------------------------------------------------------------
+  const float* d_q_full = d_q;
+  if (q_is_slice) {
+    prof.begin("scatter_queries");
+    a.done = ex->d_done + 1;
+    const uint64_t n_floats = q_n * s->dim;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(148, (n_floats / 4 + 255) / 256));
+    scatter_queries_kernel<<<blocks, 256, 0, st>>>(a, d_q, n_floats, q_lo * s->dim);
+    SCN_LAUNCHED();
+    wait_flags_kernel<<<1, 32, 0, st>>>(flag_of(ex->local, FLAG_QUERIES, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
+    SCN_LAUNCHED();
+    prof.end();
+    d_q_full = queries_of(ex->local, a.L, a.parity);
+  }
+
+  // ---- 2. shard-local search of the whole batch ---------------------------------------------------
+  uint64_t* d_keys = nullptr;
+  SCN_TRY(scratch.alloc(&d_keys, nq * k));
+  SCN_TRY(flat_keys(s, d_q_full, nq, k, row_base, d_keys, st, &prof));
+
+  // ---- 3. push each list to the owner of its query's slice -----------------------------------------
   a.done = ex->d_done;
   prof.begin("push_results");
-  const unsigned blocks = (unsigned)std::min<uint64_t>(148, (a.n + 255) / 256);
-  push_results_kernel<<<blocks, 256, 0, st>>>(a);
+  const uint64_t n = nq * k;
+  const unsigned blocks = (unsigned)std::min<uint64_t>(148, (n / 2 + 255) / 256 + 1);
+  push_results_kernel<<<blocks, 256, 0, st>>>(a, d_keys, s->d_ids, n, k, per, (uint32_t)row_base);
   SCN_LAUNCHED();
   prof.end();
+
+  // ---- 4. wait for the peers, merge this rank's slice from local memory -----------------------------
   prof.begin("wait_peers");
-  wait_flags_kernel<<<1, 32, 0, st>>>(flags_of(ex->local), ex->world, a.parity, a.epoch, ex->d_status, 5000000000ull);
+  wait_flags_kernel<<<1, 32, 0, st>>>(flag_of(ex->local, FLAG_LISTS, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
   SCN_LAUNCHED();
   prof.end();
-  prof.begin("merge_topk");
-  SCN_TRY(merge_topk(keys_of(ex->local, a.parity, ex->world, 0, a.le), ids_of(ex->local, a.parity, ex->world, 0, a.le), ex->world, nq, k,
-                     d_out_ids, d_out_dist, d_out_counts, st, a.le));
-  prof.end();
+  if (q_n) {
+    prof.begin("merge_topk");
+    SCN_TRY(merge_topk(keys_of(ex->local, a.L, a.parity, 0), ids_of(ex->local, a.L, a.parity, 0), ex->world, q_n, k, d_out_ids, d_out_dist,
+                       d_out_counts, st, a.L.le, ex->d_status));
+    prof.end();
+  }
   prof.collect();
   return SCN_OK;
 }
 
-// 0 = every wait so far was satisfied; 1 = a peer did not arrive within the time-out (results of
-// that call are invalid). Synchronises the stream first.
+// Synchronises `stream`; SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out since the
+// previous call of this function (the results of such a call are empty). Clears the status.
 int32_t scn_exchange_status(scn_exchange* ex, void* stream) {
   if (!ex) return fail(SCN_ERR_INVALID_PARAMETERS, "exchange is NULL");
   DeviceGuard g(ex->device);
   uint32_t v = 0;
   SCN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   SCN_CUDA(cudaMemcpy(&v, ex->d_status, sizeof v, cudaMemcpyDeviceToHost));
-  if (v) return fail(SCN_ERR_SEARCH_FAILED, "a peer shard did not deliver its top-k lists within 5 s");
+  if (v) {
+    SCN_CUDA(cudaMemset(ex->d_status, 0, sizeof v));
+    return fail(SCN_ERR_SEARCH_FAILED, "a peer shard did not deliver its part of the exchange within 5 s");
+  }
   return SCN_OK;
+}
+
+// Host-buffer form of one rank's call: q_slice is this rank's slice of the batch (host memory,
+// scn_exchange_slice(ex, nq, rank)), the outputs receive the results of that slice. Blocking.
+int32_t scn_search_flat_exchange(scn_store* s, scn_exchange* ex, const float* q_slice, uint64_t nq, uint32_t k, uint64_t row_base,
+                                 uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+  if (!s || !ex) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  if (ex->dim != s->dim) return fail(SCN_ERR_INVALID_PARAMETERS, "the exchange was created for dim %u, the store has %u", ex->dim, s->dim);
+  uint64_t q_lo = 0, q_n = 0;
+  SCN_TRY(scn_exchange_slice(ex, nq, ex->rank, &q_lo, &q_n));
+  if (q_n && (!q_slice || !out_ids || !out_dist)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  DeviceGuard g(s->device);
+  cudaStream_t st = thread_stream(s->device);
+  Scratch scratch(st);
+  float* d_q = nullptr;
+  uint64_t* d_ids = nullptr;
+  float* d_dist = nullptr;
+  uint32_t* d_counts = nullptr;
+  SCN_TRY(scratch.alloc(&d_q, std::max<uint64_t>(q_n, 1) * s->dim));
+  SCN_TRY(scratch.alloc(&d_ids, std::max<uint64_t>(q_n, 1) * k));
+  SCN_TRY(scratch.alloc(&d_dist, std::max<uint64_t>(q_n, 1) * k));
+  SCN_TRY(scratch.alloc(&d_counts, std::max<uint64_t>(q_n, 1)));
+  if (q_n) SCN_TRY(copy_to_device(d_q, q_slice, q_n * s->dim * sizeof(float), st));
+  SCN_TRY(scn_search_flat_exchange_dev(s, ex, d_q, 1, nq, k, row_base, d_ids, d_dist, d_counts, st));
+  if (q_n) {
+    SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, q_n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, q_n * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_counts) SCN_CUDA(cudaMemcpyAsync(out_counts, d_counts, q_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  }
+  return scn_exchange_status(ex, st);
 }
 
 }  // extern "C"

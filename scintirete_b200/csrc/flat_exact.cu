@@ -520,10 +520,18 @@ int32_t vector_ops(int32_t op, const float* d_a, const float* d_b, uint64_t n, u
 __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ ids,
                                                          uint32_t n_shards, uint64_t nq, uint32_t k, uint64_t shard_stride,
                                                          uint64_t* __restrict__ out_ids, float* __restrict__ out_dist,
-                                                         uint32_t* __restrict__ out_counts) {
+                                                         uint32_t* __restrict__ out_counts, const uint32_t* __restrict__ status) {
   uint64_t q = (uint64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nq) return;
+  if (status && *status != 0) {  // a peer never delivered its lists: no result is better than a partial one
+    for (uint32_t j = lane; j < k; j += 32) {
+      out_ids[q * k + j] = 0;
+      out_dist[q * k + j] = __int_as_float(0x7f800000);
+    }
+    if (lane == 0 && out_counts) out_counts[q] = 0;
+    return;
+  }
   // each lane owns shards lane, lane+32, ...; heads advance as winners are emitted
   uint32_t head[8];  // supports up to 256 shards
 #pragma unroll
@@ -570,11 +578,12 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint64_t* __restr
 }
 
 int32_t merge_topk(const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq, uint32_t k,
-                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, uint64_t shard_stride) {
+                   uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, uint64_t shard_stride,
+                   const uint32_t* d_status) {
   if (nq == 0) return SCN_OK;
   if (n_shards == 0 || n_shards > 256) return fail(SCN_ERR_INVALID_PARAMETERS, "n_shards must be in [1, 256]");
   merge_topk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, stream>>>(d_keys, d_ids, n_shards, nq, k, shard_stride ? shard_stride : nq * k,
-                                                                  d_out_ids, d_out_dist, d_out_counts);
+                                                                  d_out_ids, d_out_dist, d_out_counts, d_status);
   SCN_LAUNCHED();
   return SCN_OK;
 }

@@ -360,7 +360,7 @@ int32_t scn_store_load_rdb(const char* path, const char* database, const char* c
   rc = scn_graph_upload(s, m_param, inf.max_layer, entry, n, ids.data(), list_counts.data(), edge_counts.data(), edges.data());
   if (rc != SCN_OK) return bail(rc);
   if (!dead.empty()) {
-    rc = scn_store_mark_deleted(s, dead.data(), dead.size());
+    rc = scn_store_restore_deleted(s, dead.data(), dead.size());  // entry point and maxLayer stay verbatim (hnsw.go:791-793)
     if (rc != SCN_OK) return bail(rc);
   }
   *out = s;

@@ -48,16 +48,66 @@ int static_smem_of(const void* kernel) {
   return (int)fa.sharedSizeBytes;
 }
 
-cudaStream_t thread_stream(int device) {
-  // one non-blocking stream per (host thread, device): concurrent Search calls from different
-  // goroutines/threads overlap on the GPU (the reference allows concurrent readers, hnsw.go:293)
-  static thread_local cudaStream_t streams[64] = {};
-  if (device < 0 || device >= 64) return nullptr;
-  if (!streams[device]) {
-    DeviceGuard g(device);
-    cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+// Per-thread CUDA resources: one non-blocking stream per device (concurrent Search calls from
+// different goroutines/threads overlap on the GPU; the reference allows concurrent readers,
+// hnsw.go:293) and two pinned staging chunks for pageable callers. Released when the thread ends
+// (cgo calls run on whatever OS thread the Go scheduler picks, and those threads come and go).
+struct ThreadResources {
+  cudaStream_t streams[64] = {};
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  bool stage_busy[2] = {false, false};
+  ~ThreadResources() {
+    // best effort: at process exit the driver may already be gone, errors are ignored
+    for (int d = 0; d < 64; ++d)
+      if (streams[d]) cudaStreamDestroy(streams[d]);
+    for (int b = 0; b < 2; ++b) {
+      if (stage_ev[b]) cudaEventDestroy(stage_ev[b]);
+      if (stage[b]) cudaFreeHost(stage[b]);
+    }
+    cudaGetLastError();
   }
-  return streams[device];
+};
+static thread_local ThreadResources g_thread;
+
+cudaStream_t thread_stream(int device) {
+  if (device < 0 || device >= 64) return nullptr;
+  if (!g_thread.streams[device]) {
+    DeviceGuard g(device);
+    cudaStreamCreateWithFlags(&g_thread.streams[device], cudaStreamNonBlocking);
+  }
+  return g_thread.streams[device];
+}
+
+constexpr size_t STAGE_CHUNK = (size_t)4 << 20;
+
+int32_t copy_to_device(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return SCN_OK;
+  cudaPointerAttributes at{};
+  const bool known = cudaPointerGetAttributes(&at, h_src) == cudaSuccess;
+  if (!known) cudaGetLastError();
+  if ((known && at.type != cudaMemoryTypeUnregistered) || bytes <= (64u << 10)) {
+    SCN_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyDefault, stream));
+    return SCN_OK;
+  }
+  ThreadResources& t = g_thread;
+  for (int b = 0; b < 2; ++b) {
+    if (!t.stage[b]) {
+      SCN_CUDA(cudaHostAlloc(&t.stage[b], STAGE_CHUNK, cudaHostAllocPortable));
+      SCN_CUDA(cudaEventCreateWithFlags(&t.stage_ev[b], cudaEventDisableTiming));
+    }
+  }
+  size_t off = 0;
+  for (int b = 0; off < bytes; b ^= 1) {
+    const size_t n = std::min(STAGE_CHUNK, bytes - off);
+    if (t.stage_busy[b]) SCN_CUDA(cudaEventSynchronize(t.stage_ev[b]));  // the DMA that last read this chunk
+    std::memcpy(t.stage[b], static_cast<const unsigned char*>(h_src) + off, n);
+    SCN_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(d_dst) + off, t.stage[b], n, cudaMemcpyHostToDevice, stream));
+    SCN_CUDA(cudaEventRecord(t.stage_ev[b], stream));
+    t.stage_busy[b] = true;
+    off += n;
+  }
+  return SCN_OK;
 }
 
 void Profiler::collect() {
@@ -234,6 +284,22 @@ extern "C" {
 const char* scn_last_error(void) { return g_last_error.c_str(); }
 uint64_t scn_launch_count(void) { return g_launches.load(); }
 
+int32_t scn_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(SCN_ERR_INVALID_PARAMETERS, "out is NULL");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SCN_ERR_RESOURCE, "pinned host allocation of %llu bytes failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+  }
+  return SCN_OK;
+}
+
+int32_t scn_host_free(void* p) {
+  if (p) SCN_CUDA(cudaFreeHost(p));
+  return SCN_OK;
+}
+
 int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store** out) {
   if (!out) return fail(SCN_ERR_INVALID_PARAMETERS, "out is NULL");
   *out = nullptr;
@@ -330,11 +396,11 @@ static int32_t append_common(scn_store* s, const float* src, bool src_on_device,
   std::vector<uint64_t> auto_buf;
   if (ids) {
     bool still_auto = s->auto_ids;
-    for (uint64_t i = 0; i < n && still_auto; ++i) still_auto = (ids[i] == s->rows + i + 1);
+    for (uint64_t i = 0; i < n && still_auto; ++i) still_auto = (ids[i] == s->auto_base + s->rows + i + 1);
     if (!still_auto) {
       if (s->auto_ids) {  // materialise the implicit map
         s->row_of.reserve((size_t)(s->rows + n) * 2);
-        for (uint64_t r = 0; r < s->rows; ++r) s->row_of[r + 1] = (uint32_t)r;
+        for (uint64_t r = 0; r < s->rows; ++r) s->row_of[s->auto_base + r + 1] = (uint32_t)r;
         s->auto_ids = false;
       }
       for (uint64_t i = 0; i < n; ++i) {
@@ -355,13 +421,13 @@ static int32_t append_common(scn_store* s, const float* src, bool src_on_device,
     if (!s->auto_ids) {
       // explicit ids were used before: auto ids continue from row+1 only if free
       for (uint64_t i = 0; i < n; ++i)
-        if (s->row_of.count(s->rows + i + 1))
+        if (s->row_of.count(s->auto_base + s->rows + i + 1))
           return fail(SCN_ERR_INVALID_PARAMETERS, "auto id %llu collides with an explicit id",
-                      (unsigned long long)(s->rows + i + 1));
-      for (uint64_t i = 0; i < n; ++i) s->row_of[s->rows + i + 1] = (uint32_t)(s->rows + i);
+                      (unsigned long long)(s->auto_base + s->rows + i + 1));
+      for (uint64_t i = 0; i < n; ++i) s->row_of[s->auto_base + s->rows + i + 1] = (uint32_t)(s->rows + i);
     }
     auto_buf.resize(n);
-    for (uint64_t i = 0; i < n; ++i) auto_buf[i] = s->rows + i + 1;
+    for (uint64_t i = 0; i < n; ++i) auto_buf[i] = s->auto_base + s->rows + i + 1;
     ids = auto_buf.data();
   }
   int32_t rc = ensure_capacity(s, s->rows + n);
@@ -395,7 +461,10 @@ int32_t scn_store_append_dev(scn_store* s, const float* d_vecs, const uint64_t* 
   return append_common(s, d_vecs, true, ids, n);
 }
 
-int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
+// keep_entry: restore semantics — ImportGraphState takes entrypoint / maxLayer verbatim (hnsw.go:791-793),
+// so a snapshot whose entry point is flagged deleted keeps it (and Search then returns nothing, like
+// the reference: searchLayer drops a deleted entry point, hnsw.go:492-502).
+static int32_t mark_deleted_impl(scn_store* s, const uint64_t* ids, uint64_t n, bool keep_entry) {
   if (!s) return fail(SCN_ERR_INVALID_PARAMETERS, "store is NULL");
   if (n == 0) return SCN_OK;
   DeviceGuard g(s->device);
@@ -422,7 +491,7 @@ int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
   // hnsw.go:280-283: the entry point was deleted -> findNewEntrypoint (617-634): the live node with
   // the highest getNodeLayer becomes the entry point and its layer the new maxLayer. (The reference
   // walks a Go map, i.e. ties fall in random order; here, as in the oracle, in insertion order.)
-  if (s->has_graph && s->entry_row != ROW_NONE && ((bits[s->entry_row >> 5] >> (s->entry_row & 31)) & 1u)) {
+  if (!keep_entry && s->has_graph && s->entry_row != ROW_NONE && ((bits[s->entry_row >> 5] >> (s->entry_row & 31)) & 1u)) {
     int best = -1;
     uint32_t best_row = ROW_NONE;
     const uint64_t n_graph = std::min<uint64_t>(s->graph_nodes, s->h_node_layer.size());
@@ -441,6 +510,9 @@ int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) {
   // the tensor filter learns about deletions through its per-row additive term (+Inf)
   return mark_aux_deleted(s, rows.data(), (uint32_t)rows.size(), st);
 }
+
+int32_t scn_store_mark_deleted(scn_store* s, const uint64_t* ids, uint64_t n) { return mark_deleted_impl(s, ids, n, false); }
+int32_t scn_store_restore_deleted(scn_store* s, const uint64_t* ids, uint64_t n) { return mark_deleted_impl(s, ids, n, true); }
 
 // Collection.Compact (collection.go:283-313): drop the soft-deleted vectors for good. Surviving
 // rows keep their insertion order (and their ids); the graph is dropped, because the reference
@@ -469,7 +541,7 @@ int32_t scn_store_compact(scn_store* s, uint64_t* out_removed) {
   }
   std::unordered_map<uint64_t, uint32_t> row_of;
   row_of.reserve(n_new * 2);
-  for (uint64_t i = 0; i < n_new; ++i) row_of[s->auto_ids ? (uint64_t)src_row[i] + 1 : old_ids[src_row[i]]] = (uint32_t)i;
+  for (uint64_t i = 0; i < n_new; ++i) row_of[s->auto_ids ? s->auto_base + (uint64_t)src_row[i] + 1 : old_ids[src_row[i]]] = (uint32_t)i;
   uint32_t* d_src = nullptr;
   SCN_CUDA(cudaMalloc(&d_src, std::max<uint64_t>(n_new, 1) * sizeof(uint32_t)));
   SCN_CUDA(cudaMemcpy(d_src, src_row.data(), n_new * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -528,6 +600,15 @@ int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, float* out)
   std::vector<uint32_t> rows(n);
   for (uint64_t i = 0; i < n; ++i) {
     if (!s->lookup(ids[i], &rows[i])) return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);
+  }
+  if (s->live != s->rows) {  // HNSW.Get: a soft-deleted node is "not found" (hnsw.go:364-366)
+    const size_t words = (s->rows + 31) / 32;
+    std::vector<uint32_t> bits(words);
+    SCN_CUDA(cudaMemcpyAsync(bits.data(), s->d_deleted, words * 4, cudaMemcpyDeviceToHost, st));
+    SCN_CUDA(cudaStreamSynchronize(st));
+    for (uint64_t i = 0; i < n; ++i)
+      if ((bits[rows[i] >> 5] >> (rows[i] & 31)) & 1u)
+        return fail(SCN_ERR_VECTOR_NOT_FOUND, "vector %llu not found", (unsigned long long)ids[i]);
   }
   if (n <= 4) {  // HNSW.Get of one vector: straight copies
     for (uint64_t i = 0; i < n; ++i)
@@ -656,8 +737,6 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_hnsw_per_sm = value;
   } else if (n == "hnsw_early") {
     s->opt_hnsw_early = value;
-  } else if (n == "hnsw_rank") {
-    s->opt_hnsw_rank = value;
   } else if (n == "hnsw_hash") {
     s->opt_hnsw_hash = value;
   } else if (n == "tensor_hint") {
@@ -666,6 +745,10 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_bn = value;
   } else if (n == "tensor_chunks") {
     s->opt_tensor_chunks = value;
+  } else if (n == "auto_id_base") {
+    // a row shard of a larger collection: auto-assigned ids are value + row + 1 (global row + 1)
+    if (s->rows != 0 || value < 0) return fail(SCN_ERR_INVALID_PARAMETERS, "auto_id_base can only be set on an empty store");
+    s->auto_base = (uint64_t)value;
   } else if (n == "profile") {
     s->opt_profile = value;
   } else {

@@ -44,7 +44,8 @@ struct scn_store {
   // re-scanned exactly (certificate failed); hnsw: [0] distance evaluations, [1] expansions
   unsigned long long* d_counters = nullptr;
 
-  bool auto_ids = true;  // every id so far was row+1 -> no host map needed
+  bool auto_ids = true;  // every id so far was auto_base+row+1 -> no host map needed
+  uint64_t auto_base = 0;  // first auto id - 1 (a row shard of a larger collection starts at its global row)
   std::unordered_map<uint64_t, uint32_t> row_of;
 
   // graph
@@ -70,7 +71,6 @@ struct scn_store {
   int64_t opt_hnsw_global = 1;    // hnsw_search: 1 = visited tables of the first pass in global memory (L2) instead of shared memory
   int64_t opt_hnsw_per_sm = 0;    // hnsw_search, global tables: cap on resident queries per SM; 0 = whatever fits
   int64_t opt_hnsw_early = 1;     // hnsw_search: rows requested before the visited test (copies overlap the probes)
-  int64_t opt_hnsw_rank = 1;      // hnsw_search, global tables: 1 = MATCH.ANY ranks the lanes of a group, 0 = shuffles
   int64_t opt_hnsw_hash = 0;      // hnsw_search: entries of the visited table of the first pass (shared or global memory); 0 = auto
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
@@ -89,8 +89,8 @@ struct scn_store {
   uint64_t device_bytes() const;
   bool lookup(uint64_t id, uint32_t* row) const {
     if (auto_ids) {
-      if (id == 0 || id > rows) return false;
-      *row = (uint32_t)(id - 1);
+      if (id <= auto_base || id - auto_base > rows) return false;
+      *row = (uint32_t)(id - auto_base - 1);
       return true;
     }
     auto it = row_of.find(id);
@@ -163,6 +163,11 @@ struct Profiler {
 };
 
 cudaStream_t thread_stream(int device);
+// Host -> device copy of a caller's buffer, enqueued on `stream`. Pinned / registered memory is
+// copied directly; pageable memory (a Go slice, a numpy array) goes through two pinned staging
+// chunks of this thread, so that the host-side memcpy of one chunk overlaps the DMA of the previous
+// one. Either way the caller's buffer has been read completely when the function returns.
+int32_t copy_to_device(void* d_dst, const void* h_src, size_t bytes, cudaStream_t stream);
 
 // kernels / launchers implemented in the other translation units
 int32_t launch_prepare_rows(scn_store* s, uint64_t first_row, uint64_t n, cudaStream_t stream);
@@ -187,7 +192,8 @@ int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const floa
                        float* d_out, cudaStream_t stream);
 int32_t merge_topk(const uint64_t* d_keys, const uint64_t* d_ids, uint32_t n_shards, uint64_t nq, uint32_t k,
                    uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream,
-                   uint64_t shard_stride = 0 /* elements between shard lists; 0 = nq*k */);
+                   uint64_t shard_stride = 0 /* elements between shard lists; 0 = nq*k */,
+                   const uint32_t* d_status = nullptr /* non-zero word: the lists are incomplete -> empty results */);
 int32_t flat_keys(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_keys,
                   cudaStream_t stream, Profiler* prof);
 

@@ -181,6 +181,11 @@ class DeviceStore:
         a = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
         _check(_native.lib().scn_store_mark_deleted(self._h, _ptr(a), a.size))
 
+    def restore_deleted(self, ids):
+        """Soft-delete flags of a restored snapshot: entry point / maxLayer stay verbatim (hnsw.go:791-793)."""
+        a = np.ascontiguousarray(ids, dtype=np.uint64).ravel()
+        _check(_native.lib().scn_store_restore_deleted(self._h, _ptr(a), a.size))
+
     def compact(self) -> int:
         """Collection.Compact (collection.go:283-313), device half: drops the soft-deleted rows and the
         graph; returns the number of rows removed."""
@@ -287,6 +292,32 @@ class Batcher:
         return {"calls": int(c[0]), "batches": int(c[1]), "launches": int(c[2]), "max_batch": int(c[3])}
 
 
+class PinnedBuffer:
+    """A page-locked host buffer from scn_host_alloc, exposed as a numpy array (query / result
+    buffers of the host-buffer entry points are DMA-ed directly from pinned memory)."""
+
+    def __init__(self, shape, dtype):
+        self._dtype = np.dtype(dtype)
+        self._nbytes = int(np.prod(shape)) * self._dtype.itemsize
+        p = C.c_void_p()
+        _check(_native.lib().scn_host_alloc(self._nbytes, C.byref(p)))
+        self._p = p
+        buf = (C.c_char * max(self._nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self._dtype, count=int(np.prod(shape))).reshape(shape)
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def close(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p:
+            self.array = None
+            _native.lib().scn_host_free(p)
+
+    __del__ = close
+
+
 # ---- VectorIndex / HNSWIndex ---------------------------------------------------------------------
 
 class _GPUIndexBase:
@@ -321,7 +352,12 @@ class _GPUIndexBase:
         e = _f32(vector.elements)
         if vector.id == 0 or self._has(vector.id):
             raise ScintireteError(ErrorCode.INSERT_FAILED, f"failed to insert vector {vector.id}")  # hnsw.go:181-183
-        self.store.append(e[None, :], [vector.id])
+        try:
+            self.store.append(e[None, :], [vector.id])
+        except ScintireteError as err:
+            if err.code == ErrorCode.INVALID_PARAMETERS:   # e.g. the id of a soft-deleted node: still "already exists"
+                raise ScintireteError(ErrorCode.INSERT_FAILED, f"failed to insert vector {vector.id}") from err
+            raise
         if vector.metadata:
             self._metadata[vector.id] = vector.metadata
 
@@ -436,7 +472,7 @@ class GPUHNSWIndex(_GPUIndexBase):
         self.store.graph_upload(state)
         if state.deleted is not None and np.any(state.deleted):
             dead = np.asarray(state.node_ids)[np.asarray(state.deleted).astype(bool)]
-            self.store.mark_deleted(dead)
+            self.store.restore_deleted(dead)
             self._deleted.update(int(x) for x in dead)
         self._graph = state
 

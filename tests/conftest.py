@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Several tests drive G "ranks" of the fused shard exchange on ONE GPU, each on its own stream, and a
+# rank's wait kernel spins until the other ranks' kernels have run: give every stream its own
+# hardware queue so that no rank is queued behind another rank's wait (must be set before CUDA starts).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -222,3 +222,29 @@ def test_vector_helpers_batched_bit_exact():
         assert dot[i] == oracle.dot(a[i], b[i])
         assert np.array_equal(nrm[i], oracle.normalize(a[i]))
     assert np.array_equal(nrm[5], a[5]) and mag[5] == 0
+
+
+def test_pinned_and_pageable_host_buffers_give_the_same_answer():
+    # scn_host_alloc buffers are DMA-ed directly; a pageable buffer (what a Go []float32 is) goes
+    # through the library's pinned staging chunks (several chunks at this size). Same bits either way.
+    import ctypes as C
+
+    from scintirete_b200 import PinnedBuffer, _native
+    from scintirete_b200.index import _check
+
+    n, d, nq, k = 20000, 768, 4000, 10          # 12.3 MB of queries: three staging chunks
+    db, q = gaussian(n, d, 21), gaussian(nq, d, 22)
+    s = DeviceStore(d, DistanceMetric.COSINE)
+    s.append(db)
+    ids_p, dist_p, cnt_p = s.search_flat(q, k)   # pageable numpy buffers
+    pq, pi, pd, pc = PinnedBuffer((nq, d), np.float32), PinnedBuffer((nq, k), np.uint64), PinnedBuffer((nq, k), np.float32), \
+        PinnedBuffer((nq,), np.uint32)
+    pq.array[:] = q
+    _check(_native.lib().scn_search_flat(s.handle, C.c_void_p(pq.ptr), nq, k, C.c_void_p(pi.ptr), C.c_void_p(pd.ptr),
+                                         C.c_void_p(pc.ptr)))
+    assert np.array_equal(pi.array, ids_p) and np.array_equal(pd.array, dist_p) and np.array_equal(pc.array, cnt_p)
+    o = oracle.flat_search(2, db, q[:64], k, nthreads=8)
+    assert np.array_equal(ids_p[:64], o[0]) and np.array_equal(dist_p[:64], o[1])
+    for b in (pq, pi, pd, pc):
+        b.close()
+    s.close()

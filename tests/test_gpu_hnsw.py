@@ -195,3 +195,28 @@ def test_deleting_the_entry_point_picks_a_new_one_like_the_reference():
         ids, dist, cnt = g.search_batch(q, SearchParams(top_k=10, ef_search=64))
         assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist)
         assert not np.isin(ids, [ep]).any()
+
+
+def test_restored_snapshot_keeps_a_deleted_entry_point_verbatim():
+    # ImportGraphState takes entrypoint / maxLayer verbatim (hnsw.go:791-793): a snapshot whose entry
+    # point is flagged deleted answers every search with nothing (searchLayer drops the deleted entry
+    # point, hnsw.go:492-502), in the reference, in the oracle and here — no new entry point is picked.
+    n, d = 1500, 24
+    db, h, g = _pair(DistanceMetric.L2, n, d, efc=60)
+    st = h.export_graph_state()
+    st.deleted[int(st.entrypoint) - 1] = 1          # ids are 1..n in insertion order
+    st.deleted[7] = 1
+    h2 = oracle.OracleHNSW(M=16, ef_construction=60, ef_search=32, max_layers=16, seed=42, metric=1)
+    h2.import_graph_state(st)
+    g2 = GPUHNSWIndex(HNSWParams(m=16, ef_search=32), DistanceMetric.L2, d)
+    g2.import_graph_state(to_graph_state(st, 16))
+    assert g2.store.stats().entry_id == st.entrypoint and g2.get_layers() == st.max_layer + 1
+    q = gaussian(20, d, 3)
+    o_ids, o_dist, o_cnt, _ = h2.search_batch(q, 5, 32)
+    ids, dist, cnt = g2.search_batch(q, SearchParams(top_k=5, ef_search=32))
+    assert not o_cnt.any() and np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids)
+    # the raw C-ABI get hides soft-deleted rows like HNSW.Get (hnsw.go:364-366)
+    with pytest.raises(ScintireteError) as e:
+        g2.store.get([8])
+    assert e.value.code == 3004
+    assert np.array_equal(g2.store.get([9])[0], db[8])
