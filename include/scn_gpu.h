@@ -17,6 +17,7 @@
  *   BatchDistance + stable sort (flat / exact scan)        scn_search_flat[_dev]      (distance.go:144-150)
  *   HNSW.Search rerank step on caller-chosen candidates    scn_rerank                 (hnsw.go:317-347)
  *   DistanceCalculator.Distance / BatchDistance            scn_distance_batch         (distance.go:21-32, 53-82, 104-116, 144-150)
+ *   HNSW.Insert / Build (graph construction half)          scn_hnsw_insert            (hnsw.go:190-257, 560-614)
  *   HNSW.Size / MemoryUsage / GetStatistics                scn_store_stats            (hnsw.go:375-443)
  *   per-shard top-k merge (new: row-sharded multi-GPU)     scn_merge_topk_dev, scn_search_flat_exchange[_dev]
  *   VectorIndex.Search over a collection sharded over G GPUs scn_shards_search_flat     (interfaces.go:87-111)
@@ -143,6 +144,31 @@ SCN_API int32_t scn_store_get(scn_store* s, const uint64_t* ids, uint64_t n, flo
 SCN_API int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uint64_t entry_id, uint64_t n_nodes,
                          const uint64_t* node_ids, const int32_t* list_counts, const uint32_t* edge_counts,
                          const uint64_t* edges);
+
+/* ---- GPU-assisted graph construction -------------------------------------------
+ * HNSW.Insert / Build with the reference's SERIAL semantics (hnsw.go:148-257: searchLayer with
+ * efConstruction, selectNeighbors 560-583, pruneConnections 586-614, entry-point rule 252-254): the
+ * next n rows of the store that are not in its graph yet (rows graph_nodes .. graph_nodes + n - 1,
+ * in append order) are inserted one after the other. The searches of a window of upcoming inserts
+ * run speculatively on the device against one snapshot; inserts are committed strictly in order and
+ * only with a search that is provably the one the serial algorithm would have run (expansion logs
+ * checked against every adjacency change since the snapshot), otherwise the insert is searched again.
+ * The resulting graph is edge for edge the one the reference's insertVector builds for the same
+ * level draws. levels[i] = selectLayer()'s draw for the i-th new node (hnsw.go:458-469), made by the
+ * caller from its own rand stream (the Go shim uses the CPU index's). m = HNSWParams.M (<= 32),
+ * 2*m <= ef_construction <= 1024. Works on an empty graph, after scn_graph_upload, and repeatedly. */
+typedef struct scn_build_stats {
+  uint64_t inserted, rounds, searches, conflicts, table_overflows;
+  uint64_t distance_evals, expansions;   /* device counters over all (speculative) searches */
+  double seconds;
+} scn_build_stats;
+SCN_API int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t m, int32_t ef_construction,
+                        scn_build_stats* stats /* may be NULL */);
+/* The store's graph as flattened core.HNSWGraphState (the layout scn_graph_upload takes), e.g. to
+ * hand a device-built graph to the host index for persistence (ExportGraphState, hnsw.go:703-746). */
+SCN_API int32_t scn_graph_export_sizes(scn_store* s, uint64_t* n_nodes, uint64_t* n_lists, uint64_t* n_edges);
+SCN_API int32_t scn_graph_export(scn_store* s, uint64_t* node_ids, int32_t* list_counts, uint32_t* edge_counts, uint64_t* edges,
+                         uint64_t* entry_id, int32_t* max_layer);
 
 /* ---- restore from an RDB snapshot ---------------------------------------------
  * Reads one collection of a snapshot written by the reference (schemas/flatbuffers/rdb.fbs,
@@ -306,6 +332,7 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory
  *   "hnsw_hash"         entries of the visited table (0 = auto); "hnsw_per_sm" cap on resident queries per SM
  *   "hnsw_early"        1 = rows requested before the visited test (default)
+ *   "build_window"      scn_hnsw_insert: inserts searched speculatively per round (0 = adaptive, 1 = none)
  *   "auto_id_base"      (empty store only) auto-assigned ids become value + row + 1: a row shard of a larger
  *                       collection numbers its rows globally
  *   "profile"           1 = record per-kernel CUDA-event timings and the device counters */

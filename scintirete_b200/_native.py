@@ -22,6 +22,12 @@ class Stats(C.Structure):
                 ("graph_edges", C.c_uint64)]
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("inserted", C.c_uint64), ("rounds", C.c_uint64), ("searches", C.c_uint64), ("conflicts", C.c_uint64),
+                ("table_overflows", C.c_uint64), ("distance_evals", C.c_uint64), ("expansions", C.c_uint64),
+                ("seconds", C.c_double)]
+
+
 class RdbInfo(C.Structure):
     _fields_ = [("metric", C.c_int32), ("dim", C.c_uint32), ("m", C.c_int32), ("ef_construction", C.c_int32),
                 ("ef_search", C.c_int32), ("max_layers", C.c_int32), ("seed", C.c_int64), ("nodes", C.c_uint64),
@@ -48,6 +54,9 @@ SIGNATURES = {
     "scn_store_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "scn_graph_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "scn_hnsw_insert": (C.c_int32, [C.c_void_p, C.c_uint64, i32p, C.c_int32, C.c_int32, C.POINTER(BuildStats)]),
+    "scn_graph_export_sizes": (C.c_int32, [C.c_void_p, u64p, u64p, u64p]),
+    "scn_graph_export": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64p, i32p]),
     "scn_search_flat": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scn_search_hnsw": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscn_gpu.so")
-SOURCES = ["store.cu", "flat_exact.cu", "flat_tensor.cu", "hnsw_search.cu", "api.cu", "batcher.cu", "rdb_reader.cu", "exchange.cu", "shards.cu"]
-HEADERS = ["common.cuh", "store.h", os.path.join("..", "..", "include", "scn_gpu.h")]
+SOURCES = ["store.cu", "flat_exact.cu", "flat_tensor.cu", "hnsw_search.cu", "api.cu", "batcher.cu", "rdb_reader.cu", "exchange.cu", "shards.cu", "hnsw_build.cu"]
+HEADERS = ["common.cuh", "store.h", "visited.cuh", os.path.join("..", "..", "include", "scn_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

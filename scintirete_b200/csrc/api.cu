@@ -134,7 +134,11 @@ int32_t scn_search_hnsw(scn_store* s, const float* q, uint64_t nq, uint32_t k, u
   SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (out_counts) SCN_CUDA(cudaMemcpyAsync(out_counts, d_counts, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  unsigned long long failed = 0;
+  SCN_CUDA(cudaMemcpyAsync(&failed, s->d_counters + 3, sizeof failed, cudaMemcpyDeviceToHost, st));
   SCN_CUDA(cudaStreamSynchronize(st));
+  if (failed)
+    return fail(SCN_ERR_SEARCH_FAILED, "%llu walks visited more rows than the largest visited table holds (ef=%u)", failed, ef);
   return SCN_OK;
 }
 

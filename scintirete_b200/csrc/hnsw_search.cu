@@ -11,7 +11,11 @@
 //                      the first un-expanded entry of W" and the loop ends when there is none.
 //                      (Only exact float ties with W[ef-1] can make the two differ.)
 //   visited         -> open-addressing table of row indices, groups of four 32-bit slots, private
-//                      to the warp: in GLOBAL memory (L2-resident) by default, because the table
+//                      to the warp and EPOCH-TAGGED: an entry is (tag << row_bits) | (row + 1) and only
+//                      entries carrying the current query's tag count, so the table is cleared once
+//                      per warp and launch (and when the tag wraps) instead of once per query — at
+//                      ef = 128 that was a 64 KB store burst per query, a fifth of the kernel's DRAM
+//                      traffic. The table lives in GLOBAL memory (L2-resident) by default, because it
 //                      was what limited the number of resident queries, with a warp-collective,
 //                      atomic-free insert and group snapshots fetched ahead for the predicted next
 //                      expansion (visited_insert_warp); in shared memory with a CAS insert as the
@@ -39,6 +43,7 @@
 // the walk is a chain of dependent round trips: throughput = resident queries / per-expansion
 // latency (DESIGN.md 4.2 has the measurements behind every choice above).
 #include "store.h"
+#include "visited.cuh"
 
 namespace scn {
 
@@ -48,7 +53,6 @@ __host__ __device__ constexpr uint32_t gm_ch(int gm) { return gm == 3 ? 256u : 5
 __host__ __device__ constexpr uint32_t gm_nbuf(int gm) { return gm == 2 ? 2u : 1u; }
 __host__ __device__ constexpr uint32_t gm_bytes(int gm) { return gm == 0 ? 0u : ga_stage_bytes(gm_ch(gm), gm_nbuf(gm)); }
 constexpr int HNSW_MAX_WARPS = 2;  // warps (= queries) per CTA: 2 for the register gather, 1 for the shared-memory gather
-constexpr uint32_t HASH_EMPTY = 0u;
 
 struct HnswArgs {
   const float* vec;
@@ -72,6 +76,8 @@ struct HnswArgs {
   uint32_t nq, k, ef, ef_pad;
   uint32_t max_per_sm;     // global_first: cap on resident CTAs per SM (0 = whatever fits)
   uint32_t hash_size;      // entries per warp
+  uint32_t row_bits;       // bits of an entry that hold row + 1; the bits above hold the query tag
+  uint32_t tag_max;        // largest tag (>= 1); the table is cleared when the tag would exceed it
   uint32_t* ghash;         // global tables [warps][hash_size] when USE_GLOBAL
   uint32_t* overflow_list; // first pass: queries whose visited table overflowed (nullptr in the overflow pass)
   uint32_t* overflow_count;
@@ -79,6 +85,7 @@ struct HnswArgs {
   float* out_dist;
   uint32_t* out_counts;
   unsigned long long* stats;  // [0] distance evaluations, [1] expansions (optional)
+  unsigned long long* failed; // counts queries whose visited table overflowed in the overflow pass too (no result)
 };
 
 __host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t hash_size, bool global_hash,
@@ -87,94 +94,6 @@ __host__ __device__ inline size_t hnsw_warp_bytes(uint32_t pitch, uint32_t ef_pa
   // stage (shared-memory gather only) | hash
   return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + stage_bytes +
          (global_hash ? 0 : (size_t)hash_size * 4);
-}
-
-__device__ __forceinline__ uint32_t home_group(uint32_t row, uint32_t n_groups) { return __umulhi(row * 2654435761u, n_groups); }
-
-// visited set: open addressing over groups of four 32-bit slots (one 128-bit load per probe). Slots
-// of a group fill in order and are never emptied within a query, so a group that still has an
-// empty slot and does not hold the key proves the key absent. Returns true if `row` was inserted
-// (first visit), false if it was already there.
-template <bool GLOBAL>
-__device__ __forceinline__ uint4 ld_group(const uint32_t* p) {
-  uint4 v;
-  if (GLOBAL) {
-    // (the table is private to one warp, written with L2 atomics: only L1 must be bypassed)
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-  } else {
-    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
-  }
-  return v;
-}
-
-template <bool GLOBAL>
-__device__ __forceinline__ bool visited_insert(uint32_t* tab, uint32_t n_groups, uint32_t row) {
-  uint32_t g = home_group(row, n_groups);
-  const uint32_t key = row + 1;
-  for (uint32_t probes = 0; probes <= n_groups;) {
-    uint32_t* grp = tab + g * 4;
-    const uint4 v = ld_group<GLOBAL>(grp);
-    if (v.x == key || v.y == key || v.z == key || v.w == key) return false;
-    const int e = (v.x == HASH_EMPTY) ? 0 : (v.y == HASH_EMPTY) ? 1 : (v.z == HASH_EMPTY) ? 2 : (v.w == HASH_EMPTY) ? 3 : -1;
-    if (e >= 0) {
-      const uint32_t old = atomicCAS(grp + e, HASH_EMPTY, key);
-      if (old == HASH_EMPTY) return true;
-      if (old == key) return false;
-      continue;  // another lane took the slot: look at the same group again
-    }
-    ++probes;
-    if (++g == n_groups) g = 0;
-  }
-  return false;  // table full (guarded against by the overflow check)
-}
-
-// Warp-collective insert for a table in GLOBAL memory, where every dependent access is an L2 round
-// trip: one group load per probe round and NO atomic. The table is private to the warp, so the
-// lanes settle among themselves who takes which slot (match.any on the group index: the lanes
-// that want a slot of the same group take consecutive ones, those that do not fit move on to the
-// next group in the next round) and write with plain stores, which nobody waits for. `pre` may hold
-// the home group fetched ahead of time (valid only if nothing was inserted since). Lanes with
-// want == false only take part in the collectives. Returns true on a first visit.
-__device__ __forceinline__ bool visited_insert_warp(uint32_t* tab, uint32_t n_groups, uint32_t row, bool want, bool have_pre,
-                                                    uint4 pre, uint32_t lane) {
-  // (An adjacency list never names a row twice: scn_graph_upload drops repeats, which the
-  // reference would skip as visited anyway. So the lanes of a batch hold distinct rows.)
-  const uint32_t key = row + 1;
-  bool pending = want;
-  bool fresh = false;
-  uint32_t g = home_group(row, n_groups);
-  for (uint32_t round = 0; round <= n_groups; ++round) {
-    if (!__any_sync(0xffffffffu, pending)) break;
-    int e = 4;
-    if (pending) {
-      const uint4 v = (have_pre && round == 0) ? pre : ld_group<true>(tab + g * 4);
-      if (v.x == key || v.y == key || v.z == key || v.w == key) pending = false;
-      else e = (v.x == HASH_EMPTY) ? 0 : (v.y == HASH_EMPTY) ? 1 : (v.z == HASH_EMPTY) ? 2 : (v.w == HASH_EMPTY) ? 3 : 4;
-    }
-    // rank among the lower lanes that want a slot of the same group (31 shuffles: a third of the
-    // latency of MATCH.ANY on ~26 distinct values)
-    const uint32_t gi = (pending && e < 4) ? g : 0xFFFFFFFFu;
-    uint32_t rank = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < 31; ++j) {
-      const uint32_t gj = __shfl_sync(0xffffffffu, gi, j);
-      rank += (j < lane && gj == g) ? 1u : 0u;
-    }
-    if (pending) {
-      const uint32_t slot = (uint32_t)e + rank;
-      if (slot < 4) {
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(tab + g * 4 + slot), "r"(key) : "memory");
-        pending = false;
-        fresh = true;
-      } else if (++g == n_groups) {
-        g = 0;
-      }
-    }
-    __syncwarp();  // this round's stores are ordered before the next round's (and the next batch's) loads
-  }
-  return fresh;
 }
 
 template <int METRIC, bool USE_GLOBAL, int GM>
@@ -202,12 +121,19 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
   const uint32_t nq = a.qlist ? min(*a.nq_dev, a.nq) : a.nq;
   const float INF = __int_as_float(0x7f800000);
   unsigned long long evals = 0, hops = 0;
+  const uint32_t row_bits = a.row_bits;
+  uint32_t tag = 0;  // 0 = the table has not been cleared yet (scratch memory holds garbage)
 
   for (uint32_t qslot = warp_global; qslot < nq; qslot += warps_total) {
     const uint32_t qi = a.qlist ? a.qlist[qslot] : qslot;
     __syncwarp();
     stage_query(sq, a.q + (size_t)qi * a.dim, a.dim, a.pitch, lane, 32);
-    for (uint32_t i = lane; i < n_groups; i += 32) reinterpret_cast<uint4*>(hash)[i] = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
+    if (tag == 0 || tag >= a.tag_max) {  // first query of this warp, or the tag wrapped: start from an empty table
+      for (uint32_t i = lane; i < n_groups; i += 32) reinterpret_cast<uint4*>(hash)[i] = make_uint4(HASH_EMPTY, HASH_EMPTY, HASH_EMPTY, HASH_EMPTY);
+      tag = 1;
+    } else {
+      ++tag;  // every entry of the previous queries is stale from here on
+    }
     __syncwarp();
     float qn = 0.0f;
     if (METRIC == M_COS) {
@@ -268,7 +194,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
                   wrow[0] = cur;
                 }
                 cnt = 1;
-                visited_insert<USE_GLOBAL>(hash, n_groups, cur);
+                if (lane == 0) visited_insert<USE_GLOBAL>(hash, n_groups, cur, (tag << row_bits) | (cur + 1), tag, row_bits);
                 __syncwarp();
                 continue;
               }
@@ -346,8 +272,8 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
           // reference order: visited? -> deleted? -> mark visited. A deleted row is never
           // inserted, so testing `deleted` first and inserting only live rows is equivalent.
           if (ok && a.has_deleted) ok = !bit_test(a.deleted, nb);
-          if (USE_GLOBAL) ok = visited_insert_warp(hash, n_groups, nb, ok, c0 == 0 && cur == pre_grp_row, pre_grp, lane);
-          else if (ok) ok = visited_insert<false>(hash, n_groups, nb);
+          if (USE_GLOBAL) ok = visited_insert_warp(hash, n_groups, nb, ok, c0 == 0 && cur == pre_grp_row, pre_grp, lane, tag, row_bits);
+          else if (ok) ok = visited_insert<false>(hash, n_groups, nb, (tag << row_bits) | (nb + 1), tag, row_bits);
           mask = __ballot_sync(0xffffffffu, ok);
           const uint32_t ns = __popc(mask);
           if (USE_GLOBAL && c0 + 32 >= list_len) {
@@ -503,6 +429,10 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
       }
       continue;  // the overflow pass will produce this query's results
     }
+    if (overflow) {  // the overflow pass ran out of table as well: no result rather than a truncated beam
+      cnt = 0;
+      if (lane == 0) atomicAdd(a.failed, 1ull);
+    }
 
     // ---- result: the first min(k, |W|) entries, already in (distance, admission) order --------
     const uint32_t n_out = min(a.k, cnt);
@@ -564,9 +494,9 @@ static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& s
   b.qlist = a.overflow_list;
   b.nq_dev = a.overflow_count;
   b.overflow_list = nullptr;
-  // 8x the shared-memory table, never more than 2x the row count (a table that cannot fill up)
-  b.hash_size = (uint32_t)std::min<uint64_t>(std::min<uint64_t>((uint64_t)1 << 20, next_pow2(a.n_rows) * 2ull),
-                                             std::max<uint64_t>(next_pow2(a.hash_size) * 8ull, 1024));
+  // 2x the row count — a table that cannot fill up — capped at 4 M entries (16 MB per resident query;
+  // a walk that visits more than 3.6 M rows is reported as failed, scn_search_hnsw returns 5001)
+  b.hash_size = (uint32_t)std::min<uint64_t>((uint64_t)1 << 22, next_pow2(a.n_rows) * 2ull);
   b.hash_size = std::max<uint32_t>(b.hash_size, 1024u);
   const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
   SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GM>), smem2);
@@ -627,11 +557,17 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   // global tables cost no shared memory: 4x the entries keep the groups sparse (fewer second probe rounds)
   if (a.global_first) a.hash_size = (uint32_t)std::min<uint64_t>((uint64_t)next_pow2(a.hash_size) * 2, 1u << 16);
   if (s->opt_hnsw_hash > 0) a.hash_size = round_up((uint32_t)std::min<int64_t>(s->opt_hnsw_hash, 1 << 16), 512);
+  // visited entries: row + 1 in the low row_bits bits, the query tag above
+  if (a.n_rows >= (1u << 31)) return fail(SCN_ERR_INVALID_PARAMETERS, "HNSW search supports at most 2^31 - 1 rows per device");
+  a.row_bits = 1;
+  while ((1ull << a.row_bits) <= (uint64_t)a.n_rows) ++a.row_bits;   // row + 1 <= n_rows < 2^row_bits
+  a.tag_max = (uint32_t)((1ull << (32 - a.row_bits)) - 1);           // >= 1
   a.out_ids = d_out_ids;
   a.out_dist = d_out_dist;
   a.out_counts = d_out_counts;
   SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
   a.stats = s->opt_profile ? s->d_counters : nullptr;
+  a.failed = s->d_counters + 3;
   // shrink the table until at least one block fits
   while (!a.global_first && hnsw_warp_bytes(a.pitch, a.ef_pad, a.hash_size, false, gm_bytes(gm)) * (gm ? 1 : HNSW_MAX_WARPS) > 200 * 1024 &&
          a.hash_size > 1024)

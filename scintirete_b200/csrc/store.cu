@@ -265,6 +265,7 @@ static int32_t ensure_capacity(scn_store* s, uint64_t need) {
 }
 
 static void free_graph(scn_store* s) {
+  free_build_state(s);
   cudaFree(s->d_adj0);
   cudaFree(s->d_levels);
   cudaFree(s->d_up_off);
@@ -322,6 +323,11 @@ int32_t scn_store_create(int32_t device, uint32_t dim, int32_t metric, scn_store
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       uint64_t keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      // Never let an allocation on one stream wait for a free that is still pending on another
+      // stream: two ranks of the fused shard exchange driven on ONE device would deadlock (rank B's
+      // allocation would wait for rank A's free, which is ordered after A's wait for B's push).
+      int off = 0;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
     }
     cudaGetLastError();
   }
@@ -745,6 +751,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_bn = value;
   } else if (n == "tensor_chunks") {
     s->opt_tensor_chunks = value;
+  } else if (n == "build_window") {
+    s->opt_build_window = value;
   } else if (n == "auto_id_base") {
     // a row shard of a larger collection: auto-assigned ids are value + row + 1 (global row + 1)
     if (s->rows != 0 || value < 0) return fail(SCN_ERR_INVALID_PARAMETERS, "auto_id_base can only be set on an empty store");

@@ -23,6 +23,10 @@
 
 #include "common.cuh"
 
+namespace scn {
+struct BuildState;                       // hnsw_build.cu: host mirror of the graph under construction
+}
+
 struct scn_store {
   int32_t device = 0;
   uint32_t dim = 0;
@@ -61,6 +65,7 @@ struct scn_store {
   uint8_t* d_levels = nullptr;
   uint32_t* d_up_off = nullptr;
   uint32_t* d_adj_up = nullptr;
+  scn::BuildState* build = nullptr;   // present once the graph was built / extended on this device (scn_hnsw_insert)
 
   // options
   int64_t opt_flat_path = 0;
@@ -75,6 +80,7 @@ struct scn_store {
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
+  int64_t opt_build_window = 0;   // scn_hnsw_insert: inserts searched speculatively per round; 0 = adaptive, 1 = none (serial)
   int64_t opt_profile = 0;
 
   // introspection (protected by mu). Profiled kernels leave (name, start, stop) event triples
@@ -162,6 +168,7 @@ struct Profiler {
   ~Profiler();
 };
 
+void free_build_state(scn_store* s);
 cudaStream_t thread_stream(int device);
 // Host -> device copy of a caller's buffer, enqueued on `stream`. Pinned / registered memory is
 // copied directly; pageable memory (a Go slice, a numpy array) goes through two pinned staging

@@ -7,8 +7,9 @@ internal/core/algorithm/distance.go, on top of the C ABI in include/scn_gpu.h. T
 tested binding. All arithmetic happens on the GPU: there is no CPU fallback anywhere in here.
 
 Graph construction (HNSW.Insert/Build: searchLayer with efConstruction, selectNeighbors,
-pruneConnections — hnsw.go:190-257, 560-614) stays with the reference's CPU implementation; the
-built graph is handed over with ``import_graph_state`` exactly as persistence does on restore
+pruneConnections — hnsw.go:190-257, 560-614) is GPU-assisted with the reference's serial semantics
+(``scn_hnsw_insert``: speculative window searches on the device, in-order commits); a graph built
+elsewhere is handed over with ``import_graph_state`` exactly as persistence does on restore
 (database.go:398-493 -> hnsw.go:749-804).
 """
 from __future__ import annotations
@@ -211,6 +212,27 @@ class DeviceStore:
         ed = np.ascontiguousarray(st.edges, dtype=np.uint64)
         _check(_native.lib().scn_graph_upload(self._h, st.m, st.max_layer, st.entry_point, ids.size, _ptr(ids), _ptr(lc),
                                               _ptr(ec), _ptr(ed)))
+
+    def hnsw_insert(self, levels, m: int, ef_construction: int) -> Dict[str, Any]:
+        """GPU-assisted HNSW.Insert / Build (scn_hnsw_insert): the next len(levels) rows of the store that
+        are not in the graph yet are inserted with the reference's serial semantics (hnsw.go:190-257);
+        levels[i] = the selectLayer() draw of the i-th new node. Returns the build statistics."""
+        lv = np.ascontiguousarray(levels, dtype=np.int32).ravel()
+        st = _native.BuildStats()
+        _check(_native.lib().scn_hnsw_insert(self._h, lv.size, lv.ctypes.data_as(_native.i32p), m, ef_construction, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def graph_export(self, m: int = 16) -> GraphState:
+        """The store's graph as flattened core.HNSWGraphState (ExportGraphState, hnsw.go:703-746)."""
+        nn, nl, ne = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(_native.lib().scn_graph_export_sizes(self._h, C.byref(nn), C.byref(nl), C.byref(ne)))
+        ids = np.zeros(nn.value, np.uint64)
+        lc = np.zeros(nn.value, np.int32)
+        ec = np.zeros(nl.value, np.uint32)
+        ed = np.zeros(ne.value, np.uint64)
+        entry, ml = C.c_uint64(0), C.c_int32(-1)
+        _check(_native.lib().scn_graph_export(self._h, _ptr(ids), _ptr(lc), _ptr(ec), _ptr(ed), C.byref(entry), C.byref(ml)))
+        return GraphState(ids, lc, ec, ed, int(entry.value), int(ml.value), int(self.stats().live_rows), m=m)
 
     def set_option(self, name: str, value: int):
         _check(_native.lib().scn_set_option(self._h, name.encode(), value))
@@ -447,10 +469,37 @@ class GPUHNSWIndex(_GPUIndexBase):
         self.params = params
         self._graph: Optional[GraphState] = None
 
-    def build(self, vectors: Sequence[Vector]) -> None:
-        raise ScintireteError(ErrorCode.INDEX_BUILD_FAILED,
-                              "graph construction stays with the host HNSW (hnsw.go:148-257); "
-                              "hand the built graph over with import_graph_state")
+    def _select_layer(self) -> int:
+        """selectLayer (hnsw.go:458-469): floor(-ln(U) * 1/ln 2), capped at MaxLayers - 1. The draws come
+        from this index's own seeded generator (the Go shim uses the CPU index's math/rand stream)."""
+        if not hasattr(self, "_rng"):
+            self._rng = np.random.default_rng(self.params.seed)
+        u = max(float(self._rng.random()), 2.0 ** -53)
+        return min(int(np.floor(-np.log(u) * (1.0 / np.log(2.0)))), self.params.max_layers - 1)
+
+    def build(self, vectors: Sequence[Vector], levels=None) -> Dict[str, Any]:
+        """HNSW.Build (hnsw.go:148-174): clear, then insert every vector in slice order — the searches run
+        on the GPU, the graph is the one the reference's serial insertVector builds for the same level
+        draws (`levels`, default: this index's own selectLayer stream)."""
+        self.store.clear()
+        self._metadata.clear()
+        self._deleted.clear()
+        self._graph = None
+        if not len(vectors):
+            return {}
+        self.store.append(np.stack([_f32(v.elements) for v in vectors]), [v.id for v in vectors])
+        for v in vectors:
+            if v.metadata:
+                self._metadata[v.id] = v.metadata
+        if levels is None:
+            levels = [self._select_layer() for _ in vectors]
+        return self.store.hnsw_insert(levels, self.params.m, self.params.ef_construction)
+
+    def insert(self, vector: Vector, level: Optional[int] = None) -> None:
+        """HNSW.Insert (hnsw.go:177-187): store the vector and link it into the graph on the GPU."""
+        super().insert(vector)
+        self.store.hnsw_insert([self._select_layer() if level is None else level], self.params.m, self.params.ef_construction)
+        self._graph = None
 
     def get_parameters(self) -> HNSWParams:
         return self.params
@@ -477,6 +526,8 @@ class GPUHNSWIndex(_GPUIndexBase):
         self._graph = state
 
     def export_graph_state(self) -> Optional[GraphState]:
+        if self._graph is None and self.store.stats().has_graph:
+            self._graph = self.store.graph_export(self.params.m)
         return self._graph
 
     def get_graph_statistics(self):  # hnsw.go:404-443
