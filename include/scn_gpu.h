@@ -160,7 +160,11 @@ SCN_API int32_t scn_graph_upload(scn_store* s, int32_t m, int32_t max_layer, uin
 typedef struct scn_build_stats {
   uint64_t inserted, rounds, searches, conflicts, table_overflows;
   uint64_t distance_evals, expansions;   /* device counters over all (speculative) searches */
-  double seconds;
+  /* what ended the rounds: [0] a neighbour was added to a list expanded while W was not full, [1] an added
+   * neighbour would have been admitted, [2] an admitted neighbour left the list, [3] entry point / maxLayer
+   * moved, [4] expansion log incomplete, [5] beyond the window's pair-distance matrix */
+  uint64_t conflict_kind[6];
+  double seconds, device_seconds, commit_seconds;   /* total; waiting for the device; host commit + list upload */
 } scn_build_stats;
 SCN_API int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t m, int32_t ef_construction,
                         scn_build_stats* stats /* may be NULL */);

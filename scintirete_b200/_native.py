@@ -25,7 +25,8 @@ class Stats(C.Structure):
 class BuildStats(C.Structure):
     _fields_ = [("inserted", C.c_uint64), ("rounds", C.c_uint64), ("searches", C.c_uint64), ("conflicts", C.c_uint64),
                 ("table_overflows", C.c_uint64), ("distance_evals", C.c_uint64), ("expansions", C.c_uint64),
-                ("seconds", C.c_double)]
+                ("conflict_kind", C.c_uint64 * 6), ("seconds", C.c_double), ("device_seconds", C.c_double),
+                ("commit_seconds", C.c_double)]
 
 
 class RdbInfo(C.Structure):

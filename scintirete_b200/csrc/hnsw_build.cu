@@ -40,7 +40,7 @@
 
 namespace scn {
 
-constexpr uint32_t BUILD_LOGCAP = 512;         // expansion records kept per search
+constexpr uint32_t BUILD_LOGCAP = 2048;        // expansion records kept per search (a level-L node logs ~250 (L + 1))
 constexpr uint32_t LOG_NOT_FULL = 0xFFFFFFFFu;  // "W held fewer than ef entries": everything is admitted
 constexpr uint32_t LOG_OVERFLOW = 0xFFFFFFFFu;  // log_cnt: the visited table filled up, search unusable
 
@@ -91,69 +91,106 @@ struct BuildArgs {
 
 __host__ __device__ inline size_t build_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t stage_bytes) {
   // wkey[2][ef_pad] u64 | snk[32] u64 | q[pitch] f32 | wrow[2][ef_pad] u32 | snr[32] u32 | eps[64] u32 | stage
+  // (ef_pad = capacity of a candidate array: 2 * efConstruction, W plus ghosts)
   return (size_t)ef_pad * 16 + 256 + (size_t)pitch * 4 + (size_t)ef_pad * 8 + 128 + 256 + stage_bytes;
 }
 
-// W <- best ef of (W u admitted lanes), by rank (see hnsw_search.cu: keys are unique, so positions
-// are counted instead of sorted; ascending key order is the reference's stable insertion order).
+// ---- the candidate lists of searchLayer, exactly (ties included) -----------------------------------
+// `candidates` (W) and `dynamic` (C) of hnsw.go:487-557 live in ONE sorted array of keys
+// ord(dist) << 32 | admission_seq << 1 | expanded (ascending key order = the reference's stable
+// insertion order):
+//   positions [0, cnt)           W, cnt <= ef
+//   positions [cnt, cnt + gcnt)  "ghosts": elements that were admitted, have since been pushed out of W,
+//                                and whose distance EQUALS W[ef-1]'s. They are the only evicted members
+//                                of C the reference can still expand (it pops C in (distance, admission)
+//                                order and stops at the first one with dist > W[ef-1].dist, hnsw.go:516-518;
+//                                an evicted element never has dist < W[ef-1].dist). All of them were in W
+//                                when its last distance took its current value, so there are at most ef.
+// C's un-popped part = the un-expanded entries of [0, cnt + gcnt), in array order.
+// Admission is the reference's SEQUENTIAL rule (hnsw.go:536-542): the neighbours of a list are judged
+// one after the other against the W the previous ones left, i.e. neighbour j enters iff fewer than ef
+// elements of (W before the list) u (earlier neighbours of the list) have distance <= its own.
 struct WState {
   uint64_t *key, *okey;
   uint32_t *row, *orow;
-  uint32_t cnt, p_lo;
+  uint32_t cnt, gcnt, p_lo;
 };
-__device__ __forceinline__ void merge_admitted(WState& w, uint64_t* snk, uint32_t* snr, bool in, uint64_t key, uint32_t nb,
-                                               uint32_t ef, uint32_t lane) {
-  const uint32_t mask_in = __ballot_sync(0xffffffffu, in);
-  const uint32_t nn = __popc(mask_in);
-  if (!nn) return;
-  const uint32_t slot = __popc(mask_in & ((1u << lane) - 1u));
-  if (in) {
+
+// number of keys in k[0, n) that are < x  (k ascending)
+__device__ __forceinline__ uint32_t lower_bound_keys(const uint64_t* k, uint32_t n, uint64_t x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (k[mid] < x) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Judges the candidate lanes (`cand`: evaluated for the first time and, if W is full, closer than
+// W[ef-1] was when the list part was read) in list order, merges the admitted ones into the other
+// buffer. Returns the mask of admitted lanes.
+__device__ __forceinline__ uint32_t merge_admitted(WState& w, uint64_t* snk, uint32_t* snr, bool cand, uint64_t key, uint32_t nb,
+                                                   uint32_t ef, uint32_t cap, uint32_t lane) {
+  const uint32_t cand_mask = __ballot_sync(0xffffffffu, cand);
+  const uint32_t nc = __popc(cand_mask);
+  if (!nc) return 0u;
+  const uint32_t tot = w.cnt + w.gcnt;
+  const uint32_t slot = __popc(cand_mask & ((1u << lane) - 1u));
+  if (cand) {
     snk[slot] = key;
     snr[slot] = nb;
   }
   __syncwarp();
-  const bool mine = lane < nn;
+  // lane j < nc owns candidate j (list order)
+  const bool mine = lane < nc;
   const uint64_t nkey = mine ? snk[lane] : KEY_NONE;
-  uint32_t npos = 0;
-  for (uint32_t i0 = 0; i0 < w.cnt; i0 += 128) {
-    uint64_t kv[4];
-    uint32_t rw[4], below[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t i = i0 + u * 32 + lane;
-      kv[u] = (i < w.cnt) ? w.key[i] : KEY_NONE;
-      rw[u] = (i < w.cnt) ? w.row[i] : ROW_NONE;
-      below[u] = 0;
+  const uint32_t nord = (uint32_t)(nkey >> 32);
+  uint32_t lb = 0, le_old = 0;
+  if (mine) {
+    lb = lower_bound_keys(w.key, tot, nkey);                                           // old entries ahead of it
+    le_old = lower_bound_keys(w.key, w.cnt, ((uint64_t)nord << 32) | 0xFFFFFFFFull);   // old W entries with dist <= its own
+  }
+  // earlier candidates of the list with dist <= its own (admitted or not: one that was refused had
+  // dist >= W[ef-1] then, and W[ef-1] has not grown since)
+  uint32_t le_new = 0;
+  for (uint32_t k = 0; k < nc; ++k) {
+    const uint32_t ok_ = __shfl_sync(0xffffffffu, nord, k);
+    le_new += (k < lane && ok_ <= nord) ? 1u : 0u;
+  }
+  const bool adm = mine && (le_old + le_new < ef);
+  const uint32_t adm_mask = __ballot_sync(0xffffffffu, adm);   // over candidate slots
+  const uint32_t na = __popc(adm_mask);
+  // admitted lanes in list positions (for the log)
+  const uint32_t lanes_admitted = __ballot_sync(0xffffffffu, cand && ((adm_mask >> slot) & 1u));
+  if (!na) return 0u;
+  // position of an admitted new key: old entries ahead + admitted new keys ahead
+  uint32_t npos = lb;
+  for (uint32_t k = 0; k < nc; ++k) {
+    const uint64_t kk = snk[k];   // broadcast
+    npos += (((adm_mask >> k) & 1u) && kk < nkey) ? 1u : 0u;
+  }
+  // old entries move back by the number of admitted new keys ahead of them
+  for (uint32_t i0 = 0; i0 < tot; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const uint64_t kv = (i < tot) ? w.key[i] : KEY_NONE;
+    const uint32_t rw = (i < tot) ? w.row[i] : ROW_NONE;
+    uint32_t below = 0;
+    for (uint32_t k = 0; k < nc; ++k) {
+      const uint64_t kk = snk[k];
+      below += (((adm_mask >> k) & 1u) && kk < kv) ? 1u : 0u;
     }
-    for (uint32_t j = 0; j < nn; ++j) {
-      const uint64_t nk = snk[j];
-      uint32_t c = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool lt = nk < kv[u];
-        below[u] += lt ? 1u : 0u;
-        c += (!lt && kv[u] != KEY_NONE) ? 1u : 0u;
-      }
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == j) npos += c;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t i = i0 + u * 32 + lane;
-      const uint32_t pos = i + below[u];
-      if (i < w.cnt && pos < ef) {
-        w.okey[pos] = kv[u];
-        w.orow[pos] = rw[u];
-      }
+    const uint32_t pos = i + below;
+    if (i < tot && pos < cap) {
+      w.okey[pos] = kv;
+      w.orow[pos] = rw;
     }
   }
-  for (uint32_t j = 0; j < nn; ++j) npos += (snk[j] < nkey) ? 1u : 0u;
-  if (mine && npos < ef) {
+  if (adm && npos < cap) {
     w.okey[npos] = nkey;
     w.orow[npos] = snr[lane];
   }
-  w.p_lo = min(w.p_lo, __reduce_min_sync(0xffffffffu, mine ? npos : 0xFFFFFFFFu));
-  w.cnt = min(ef, w.cnt + nn);
+  w.p_lo = min(w.p_lo, __reduce_min_sync(0xffffffffu, adm ? npos : 0xFFFFFFFFu));
   __syncwarp();
   uint64_t* tk = w.key;
   w.key = w.okey;
@@ -161,6 +198,16 @@ __device__ __forceinline__ void merge_admitted(WState& w, uint64_t* snk, uint32_
   uint32_t* tr = w.row;
   w.row = w.orow;
   w.orow = tr;
+  const uint32_t ntot = min(cap, tot + na);
+  w.cnt = min(ef, ntot);
+  // ghosts: the run of entries right behind W[ef-1] that share its distance
+  uint32_t g = 0;
+  if (ntot > ef) {
+    const uint32_t wo = reinterpret_cast<const uint32_t*>(w.key)[2 * (ef - 1) + 1];
+    g = lower_bound_keys(w.key + ef, ntot - ef, ((uint64_t)wo << 32) | 0xFFFFFFFFull);   // every lane computes the same value
+  }
+  w.gcnt = g;
+  return lanes_admitted;
 }
 
 // One warp per pending insert: all of insertVector's searches (hnsw.go:215-226) against the current
@@ -214,7 +261,8 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
         ++tag;
       }
       __syncwarp();
-      WState w{wkey0, wkey1, wrow0, wrow1, 0u, 0u};
+      WState w{wkey0, wkey1, wrow0, wrow1, 0u, 0u, 0u};
+      const uint32_t cap = 2u * ef;   // W + ghosts (<= a.ef_pad)
       uint32_t seq = 1, visited = 0;
       // ---- entry points (hnsw.go:492-508): evaluate, mark visited, W = C = sorted(entries)
       for (uint32_t e0 = 0; e0 < n_eps && !overflow; e0 += 32) {
@@ -229,15 +277,16 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
         const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
         const uint64_t key = ((uint64_t)f32_ord(d) << 32) | ((uint64_t)(seq + rank) << 1);
         seq += __popc(mask);
-        merge_admitted(w, snk, snr, ok, key, nb, max(ef, n_eps), lane);   // entries all stay (n_eps <= ef, checked on the host)
+        merge_admitted(w, snk, snr, ok, key, nb, max(ef, n_eps), max(cap, n_eps), lane);   // entries all stay (n_eps <= ef, checked on the host)
       }
       w.p_lo = 0;
       // ---- beam (hnsw.go:510-548): expand the closest un-expanded entry of W until there is none
       while (!overflow) {
+        const uint32_t tot = w.cnt + w.gcnt;   // un-expanded ghosts are expanded after all of W (they tie with W[ef-1])
         uint32_t mm = 0, b0 = w.p_lo & ~31u;
-        for (; b0 < w.cnt; b0 += 32) {
+        for (; b0 < tot; b0 += 32) {
           const uint32_t i = b0 + lane;
-          const bool un = (i < w.cnt) && !(reinterpret_cast<const uint32_t*>(w.key)[2 * i] & 1u);
+          const bool un = (i < tot) && !(reinterpret_cast<const uint32_t*>(w.key)[2 * i] & 1u);
           mm = __ballot_sync(0xffffffffu, un);
           if (mm) break;
         }
@@ -270,14 +319,13 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
           visited += __popc(mask);
           evals += __popc(mask);
           const uint32_t od = f32_ord(d);
-          const bool in = ok && (worst == LOG_NOT_FULL || od < worst);
-          const uint32_t mask_in = __ballot_sync(0xffffffffu, in);
-          if (lane == 0 && n_log < BUILD_LOGCAP) log[n_log] = make_uint4(cur, worst, mask_in, (uint32_t)lc | ((c0 >> 5) << 8));
-          ++n_log;
+          const bool cand = ok && (worst == LOG_NOT_FULL || od < worst);   // the rest cannot be admitted: W[ef-1] only shrinks
           const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
           const uint64_t key = ((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1);
           seq += __popc(mask);
-          merge_admitted(w, snk, snr, in, key, nb, ef, lane);
+          const uint32_t mask_in = merge_admitted(w, snk, snr, cand, key, nb, ef, cap, lane);
+          if (lane == 0 && n_log < BUILD_LOGCAP) log[n_log] = make_uint4(cur, worst, mask_in, (uint32_t)lc | ((c0 >> 5) << 8));
+          ++n_log;
         }
       }
       if (overflow) break;
@@ -386,9 +434,10 @@ struct PinnedArena {
   }
 };
 
-struct Change {       // one change of a neighbour set during this round
+struct Change {       // one change of a neighbour list during this round
   uint32_t added;     // row that joined the list, or ROW_NONE
   uint32_t removed;   // row that left the list, or ROW_NONE
+  bool reordered;     // the surviving neighbours changed their relative order (first prune of a list)
 };
 
 struct RoundLog {
@@ -452,7 +501,7 @@ struct Builder {
       a[c] = nb;
       o[c] = d_ord;
       ++c;
-      if (!is_new_node) round.changes[list_key(row, layer)].push_back({nb, ROW_NONE});
+      if (!is_new_node) round.changes[list_key(row, layer)].push_back({nb, ROW_NONE, false});
       return;
     }
     // the list would hold maxConn + 1 entries: keep the closest maxConn live ones, stable by distance
@@ -475,9 +524,21 @@ struct Builder {
       for (uint32_t i = 0; i < c; ++i) {
         bool kept = false;
         for (uint32_t j = 0; j < keep && !kept; ++j) kept = all[j].row == a[i];
-        if (!kept) ch.push_back({ROW_NONE, a[i]});
+        if (!kept) ch.push_back({ROW_NONE, a[i], false});
       }
-      if (nb_kept) ch.push_back({nb, ROW_NONE});
+      if (nb_kept) ch.push_back({nb, ROW_NONE, false});
+      // did the survivors keep their relative order? (the order in which a walk meets the neighbours
+      // decides ties between equal distances)
+      uint32_t last = 0;
+      bool reordered = false;
+      for (uint32_t j = 0; j < keep && !reordered; ++j) {
+        if (all[j].row == nb) continue;
+        uint32_t pos = 0;
+        while (pos < c && a[pos] != all[j].row) ++pos;
+        reordered = pos < last;
+        last = pos;
+      }
+      if (reordered) ch.push_back({ROW_NONE, ROW_NONE, true});
     }
     for (uint32_t i = 0; i < mc; ++i) {
       a[i] = (i < keep) ? all[i].row : ROW_NONE;
@@ -492,6 +553,7 @@ struct Builder {
 // Ensures the store carries a host mirror of its graph (edge distances computed on the device) and
 // device adjacency arrays with room for `rows` rows / `lists` upper lists.
 static int32_t prepare_build_state(scn_store* s, int32_t m, cudaStream_t st) {
+  if (s->build && s->build->n_nodes == 0 && !s->has_graph) free_build_state(s);   // nothing built yet: M is still free
   if (s->build) {
     if ((int32_t)s->build->m != m) return fail(SCN_ERR_INVALID_PARAMETERS, "the graph was built with M=%u, not %d", s->build->m, m);
     return SCN_OK;
@@ -665,7 +727,7 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
   int sms = 0;
   SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   const uint32_t efc = (uint32_t)ef_construction;
-  const uint32_t ef_pad = std::max(32u, next_pow2(efc));
+  const uint32_t ef_pad = std::max(64u, round_up(2 * efc, 32));   // W + ghosts (see WState)
   const bool long_rows = s->pitch * 4 > 512;
   const size_t smem = build_warp_bytes(s->pitch, ef_pad, ga_stage_bytes(long_rows ? 512 : 256, 1));
   if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "efConstruction=%u / dim=%u need more shared memory than one SM has", efc, s->dim);
@@ -742,6 +804,8 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
   SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
 
   uint64_t done = 0, rounds = 0, searched = 0, conflicts = 0, overflowed = 0;
+  uint64_t why[6] = {0, 0, 0, 0, 0, 0};   // what ended the rounds (scn_build_stats.conflict_kind)
+  double t_device = 0.0, t_commit = 0.0;
   double avg_commits = 4.0;
   uint32_t big_hash_rounds = 0;
 
@@ -804,6 +868,7 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
       n_lists = b->level[h_qrows[0]] + 1u;
       --big_hash_rounds;
     }
+    const auto t_round = std::chrono::steady_clock::now();
     SCN_CUDA(cudaMemcpyAsync(d_qrows, h_qrows.data(), W * 4, cudaMemcpyHostToDevice, st));
     SCN_CUDA(cudaMemcpyAsync(d_qlevels, h_qlevels.data(), W, cudaMemcpyHostToDevice, st));
     SCN_CUDA(cudaMemcpyAsync(d_outoff, h_outoff.data(), W * 4, cudaMemcpyHostToDevice, st));
@@ -865,6 +930,8 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
     SCN_CUDA(cudaStreamSynchronize(st));
     ++rounds;
     searched += W;
+    const auto t_searched = std::chrono::steady_clock::now();
+    t_device += std::chrono::duration<double>(t_searched - t_round).count();
 
     // ---- commit in order while the speculative searches are provably the serial ones -----------------
     B.round.clear();
@@ -882,9 +949,11 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
       }
       // -- validation against the changes of this round
       bool valid = !B.round.global_changed;
+      int reason = 3;
       if (valid && !B.round.changes.empty()) {
         if (h_logcnt[i] > BUILD_LOGCAP || i >= P) {
           valid = false;   // the log is incomplete / no pair distances: usable only on an unchanged graph
+          reason = (i >= P) ? 5 : 4;
         } else {
           const uint4* lg = h_log + (size_t)i * BUILD_LOGCAP;
           for (uint32_t r = 0; r < h_logcnt[i] && valid; ++r) {
@@ -893,11 +962,17 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
             if (it == B.round.changes.end()) continue;
             const std::vector<uint32_t>& snap = B.round.snapshot[list_key(row, layer)];
             for (const Change& c : it->second) {
+              if (c.reordered && amask != 0) {
+                valid = false;   // the walk admitted neighbours of a list whose order has changed since
+                reason = 2;
+                break;
+              }
               if (c.added != ROW_NONE) {
                 // a node committed earlier in this round: slot index = its row - first row of the window
                 const uint32_t j = c.added - h_qrows[0];
                 if (j >= i || worst == LOG_NOT_FULL || h_pairs[(size_t)i * P + j] < worst) {
                   valid = false;
+                  reason = (worst == LOG_NOT_FULL) ? 0 : 1;
                   break;
                 }
               }
@@ -910,10 +985,12 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
                   const uint32_t j = c.removed - h_qrows[0];
                   if (j >= i || worst == LOG_NOT_FULL || h_pairs[(size_t)i * P + j] < worst) {
                     valid = false;
+                    reason = (worst == LOG_NOT_FULL) ? 0 : 1;
                     break;
                   }
                 } else if ((pos >> 5) == chunk && ((amask >> (pos & 31)) & 1u)) {
                   valid = false;   // the walk admitted a neighbour that is no longer in this list
+                  reason = 2;
                   break;
                 }
               }
@@ -923,6 +1000,7 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
       }
       if (!valid) {
         ++conflicts;
+        ++why[reason];
         break;
       }
       // -- insertVector's link phase (hnsw.go:224-254) with the lists the device search returned
@@ -952,6 +1030,7 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
     b->n_nodes = first + done;
     avg_commits = 0.75 * avg_commits + 0.25 * (double)committed;
     SCN_TRY(push_dirty());
+    t_commit += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_searched).count();
   }
 
   // ---- the store's graph fields --------------------------------------------------------------------
@@ -981,7 +1060,10 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
     stats->table_overflows = overflowed;
     stats->distance_evals = h[0];
     stats->expansions = h[1];
+    for (int i = 0; i < 6; ++i) stats->conflict_kind[i] = why[i];
     stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    stats->device_seconds = t_device;
+    stats->commit_seconds = t_commit;
   }
   return SCN_OK;
 }

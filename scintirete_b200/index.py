@@ -220,7 +220,7 @@ class DeviceStore:
         lv = np.ascontiguousarray(levels, dtype=np.int32).ravel()
         st = _native.BuildStats()
         _check(_native.lib().scn_hnsw_insert(self._h, lv.size, lv.ctypes.data_as(_native.i32p), m, ef_construction, C.byref(st)))
-        return {f: getattr(st, f) for f, _ in st._fields_}
+        return {f: (list(getattr(st, f)) if f == "conflict_kind" else getattr(st, f)) for f, _ in st._fields_}
 
     def graph_export(self, m: int = 16) -> GraphState:
         """The store's graph as flattened core.HNSWGraphState (ExportGraphState, hnsw.go:703-746)."""

@@ -146,3 +146,22 @@ def test_full_size_build_equals_the_cached_reference_graph(n, d, metric):
     print(f"\nGPU-assisted build {n}x{d}: {stats['seconds']:.1f}s, {stats['rounds']} rounds, "
           f"{stats['inserted'] / max(stats['rounds'], 1):.1f} commits/round, {stats['conflicts']} conflicts")
     s.close()
+
+
+@pytest.mark.parametrize("n,d,hi,M,efc,metric", [(3000, 8, 3, 8, 40, 1), (3000, 16, 2, 16, 64, 1), (4000, 12, 4, 16, 100, 2),
+                                                 (3000, 24, 3, 16, 200, 3), (600, 4, 1, 4, 16, 1)])
+@pytest.mark.parametrize("window", [1, 0])
+def test_exact_distance_ties_follow_the_reference(n, d, hi, M, efc, metric, window):
+    # small integer coordinates: most distances tie exactly (the last case: all vectors identical). The
+    # walk must reproduce the reference's tie rules: stable (distance, admission) order, sequential
+    # admission inside one adjacency list (strict <, hnsw.go:536-542), and candidates that were pushed out
+    # of `candidates` but still equal W[ef-1] stay expandable in `dynamic` (hnsw.go:516-518)
+    db = np.random.default_rng(5).integers(0, hi, (n, d)).astype(np.float32) + (0.0 if metric == 1 else 1.0)
+    h = _oracle(db, DistanceMetric(metric), M, efc)
+    st = h.export_graph_state()
+    s = DeviceStore(d, DistanceMetric(metric))
+    s.append(db)
+    s.set_option("build_window", window)
+    s.hnsw_insert(st.list_counts - 1, M, efc)
+    _same_graph(st, s.graph_export(M))
+    s.close()
