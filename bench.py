@@ -711,6 +711,59 @@ def bench_hnsw(ctx: Ctx, wl, name: str, ef: int, steps: int, warmup: int, cpu_ba
     return block
 
 
+def bench_build(ctx: Ctx, rows: int, dim: int, metric: int, extra: int = 2000):
+    """GPU-assisted HNSW construction (scn_hnsw_insert) on the data of a cached reference graph:
+    the whole graph is rebuilt on the GPU from the same level draws and compared edge for edge with the graph the
+    reference's serial algorithm built (oracle; bench_cache/). CPU baseline on a bounded sample: `extra` further
+    inserts into the finished graph by the oracle on one core (insertVector is serial), the same inserts on the GPU."""
+    import oracle
+    from scintirete_b200 import DeviceStore, DistanceMetric
+
+    if ctx.rank != 0:
+        return None
+    z = np.load(graph_cache_path(rows, dim, metric))
+    db = gen_rows_numpy(0, rows + extra, dim, SEED_DB)
+    store = DeviceStore(dim, DistanceMetric(metric), device=ctx.local)
+    store.append(db[:rows])
+    launches0 = ctx.lib.scn_launch_count()
+    st = store.hnsw_insert(z["list_counts"] - 1, 16, 200)
+    launches = ctx.lib.scn_launch_count() - launches0
+    g = store.graph_export(16)
+    same = bool(np.array_equal(g.node_ids, z["ids"]) and np.array_equal(g.list_counts, z["list_counts"])
+                and np.array_equal(g.edge_counts, z["edge_counts"]) and np.array_equal(g.edges, z["edges"].astype(np.uint64))
+                and g.entry_point == int(z["entrypoint"]) and g.max_layer == int(z["max_layer"]))
+    # the same `extra` inserts into the finished graph: oracle (one core) vs GPU
+    levels = np.minimum(np.floor(-np.log(np.random.default_rng(99).random(extra)) / np.log(2.0)), 15).astype(np.int32)
+    h = oracle.OracleHNSW(M=16, ef_construction=200, ef_search=128, max_layers=16, seed=42, metric=metric)
+    h.import_graph_state(oracle.GraphState(z["ids"], z["deleted"], z["list_counts"], z["edge_counts"], z["edges"].astype(np.uint64),
+                                           db[:rows], int(z["entrypoint"]), int(z["max_layer"]), int(z["size"])))
+    t0 = time.perf_counter()
+    for i in range(extra):
+        h.insert(rows + i + 1, db[rows + i], level=int(levels[i]))
+    cpu_s = time.perf_counter() - t0
+    store.append(db[rows:])
+    st2 = store.hnsw_insert(levels, 16, 200)
+    o = h.export_graph_state(with_vectors=False)
+    g2 = store.graph_export(16)
+    same2 = bool(np.array_equal(g2.edge_counts, o.edge_counts) and np.array_equal(g2.edges, o.edges)
+                 and g2.entry_point == o.entrypoint and g2.max_layer == o.max_layer)
+    store.close()
+    return {
+        "workload": f"build: {rows}x{dim} {METRIC_NAME[metric]} HNSW construction M=16 efC=200 (reference-serial semantics, GPU-assisted)",
+        "metric": "inserts/sec", "value": rows / st["seconds"], "unit": "inserts/s", "seconds": st["seconds"],
+        "rounds": st["rounds"], "commits_per_round": rows / max(st["rounds"], 1), "speculative_searches": st["searches"],
+        "rounds_ended_by": dict(zip(["added_while_not_full", "added_would_be_admitted", "admitted_neighbour_left", "entry_or_maxlayer_moved",
+                                     "log_incomplete", "beyond_pair_matrix"], st["conflict_kind"])),
+        "device_seconds": st["device_seconds"], "commit_seconds": st["commit_seconds"], "gpu_launches": int(launches),
+        "verified": {"identical": same, "against": "the cached graph the oracle (reference algorithm, serial) built from the same data and "
+                                                   "level draws: every adjacency list in stored order, entry point, maxLayer"},
+        "at_full_size": {"inserts": extra, "gpu_inserts_per_s": extra / st2["seconds"], "cpu_inserts_per_s": extra / cpu_s,
+                         "identical": same2, "note": f"the same {extra} further inserts into the finished {rows}-node graph"},
+        "cpu_baseline": {"value": extra / cpu_s, "unit": "inserts/s", "cores": 1, "kind": "port",
+                         "sample": f"{extra} inserts into the finished {rows}-node graph, {cpu_s:.1f}s (insertVector is serial: one core)"},
+    }
+
+
 def run_ours(args, wl, name):
     ctx = Ctx(args)
     rows, dim, metric, nq, k, kind = wl
@@ -725,7 +778,9 @@ def run_ours(args, wl, name):
         if ctx.world == 1 and os.path.exists(graph_cache_path(*WORKLOADS["c3"][:3])):
             secondary.append(bench_hnsw(ctx, WORKLOADS["c3"], "c3", 128, args.steps, args.warmup, not args.no_cpu_baseline,
                                         [16, 32, 64, 256, 512]))
-        elif ctx.world == 1 and ctx.rank == 0:
+        if ctx.world == 1 and os.path.exists(graph_cache_path(*WORKLOADS["c1"][:3])) and not args.no_cpu_baseline:
+            secondary.append(bench_build(ctx, *WORKLOADS["c1"][:3]))
+        if ctx.world == 1 and ctx.rank == 0 and not os.path.exists(graph_cache_path(*WORKLOADS["c3"][:3])):
             secondary.append({"workload": "c3", "skipped": "bench_cache/ holds no reference-built 1M x 128 graph on this box "
                                                            "(the serial reference construction takes hours; see DESIGN.md)"})
         if ctx.world >= 2:

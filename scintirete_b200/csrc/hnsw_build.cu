@@ -210,10 +210,54 @@ __device__ __forceinline__ uint32_t merge_admitted(WState& w, uint64_t* snk, uin
   return lanes_admitted;
 }
 
+// ---- row gather of the build walk: ALL stages of a batch in flight at once -------------------------------
+// The build runs few walks (one warp per pending insert, a window of tens) and each walk is a chain of
+// dependent expansions, so shared memory is spent on latency instead of occupancy: the rows of a batch
+// are requested in full (NB stages of 512 bytes per row, up to 6 = 3 KB rows) before anything is waited
+// for — one memory latency per expansion instead of one per stage. Longer rows go block by block.
+template <uint32_t NB>
+__device__ __forceinline__ void gather_all_begin(const float* __restrict__ vec, uint32_t pitch, uint32_t row, uint32_t mask,
+                                                 unsigned char* stage, uint32_t lane) {
+  const uint32_t n_chunks = (pitch * 4 + 511) / 512;
+  for (uint32_t ch = 0; ch < min(NB, n_chunks); ++ch) gather_issue<512, NB>(vec, pitch, row, mask, ch, stage, lane);
+}
+// completes a gather begun for a superset of `mask`; +Inf on the other lanes
+template <int METRIC, uint32_t NB>
+__device__ __forceinline__ float gather_all_finish(const float* __restrict__ vec, const float* __restrict__ norm, uint32_t pitch,
+                                                   const float* sq, float qn, uint32_t row, uint32_t mask, unsigned char* stage,
+                                                   uint32_t lane) {
+  const uint32_t row_bytes = pitch * 4;
+  const uint32_t n_chunks = (row_bytes + 511) / 512;
+  const bool valid = (mask >> lane) & 1u;
+  float acc = 0.0f;
+  const float xn = (METRIC == M_COS && valid) ? __ldg(norm + row) : 0.0f;
+  for (uint32_t c0 = 0; c0 < n_chunks; c0 += NB) {
+    cp_async_wait<0>();
+    __syncwarp();   // every lane's pieces of these stages have landed
+    if (valid) {
+      for (uint32_t ch = c0; ch < min(c0 + NB, n_chunks); ++ch) {
+        const uint32_t n4 = min(512u, row_bytes - ch * 512) / 16;
+        const float4* x4 = reinterpret_cast<const float4*>(stage + ((ch % NB) * 32 + lane) * ga_row(512));
+        const float4* q4 = reinterpret_cast<const float4*>(sq) + ch * 32;
+        if (n4 == 32) {
+#pragma unroll
+          for (uint32_t i = 0; i < 32; ++i) acc = acc_step4<METRIC>(acc, q4[i], x4[i]);
+        } else {
+          for (uint32_t i = 0; i < n4; ++i) acc = acc_step4<METRIC>(acc, q4[i], x4[i]);
+        }
+      }
+    }
+    __syncwarp();   // the buffers are free again
+    if (mask)
+      for (uint32_t ch = c0 + NB; ch < min(c0 + 2 * NB, n_chunks); ++ch) gather_issue<512, NB>(vec, pitch, row, mask, ch, stage, lane);
+  }
+  return valid ? finish_distance<METRIC>(acc, qn, xn) : __int_as_float(0x7f800000);
+}
+
 // One warp per pending insert: all of insertVector's searches (hnsw.go:215-226) against the current
 // device graph. Output: for every layer lc <= level the sorted result list W of
 // searchLayer(vec, eps, efConstruction, lc), and the expansion log of the whole walk.
-template <int METRIC, uint32_t GCH>
+template <int METRIC, uint32_t NB>
 __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
   extern __shared__ __align__(16) unsigned char smem_build[];
   const uint32_t lane = threadIdx.x;
@@ -273,13 +317,15 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
         if (!mask) continue;
         visited += __popc(mask);
         evals += __popc(mask);
-        const float d = gather_distance<METRIC, GCH, 1>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
+        gather_all_begin<NB>(a.vec, a.pitch, nb, mask, stage, lane);
+        const float d = gather_all_finish<METRIC, NB>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
         const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
         const uint64_t key = ((uint64_t)f32_ord(d) << 32) | ((uint64_t)(seq + rank) << 1);
         seq += __popc(mask);
         merge_admitted(w, snk, snr, ok, key, nb, max(ef, n_eps), max(cap, n_eps), lane);   // entries all stay (n_eps <= ef, checked on the host)
       }
       w.p_lo = 0;
+      uint32_t pre_row = ROW_NONE, pre_nb = ROW_NONE;   // layer 0: adjacency fetched ahead for the runner-up
       // ---- beam (hnsw.go:510-548): expand the closest un-expanded entry of W until there is none
       while (!overflow) {
         const uint32_t tot = w.cnt + w.gcnt;   // un-expanded ghosts are expanded after all of W (they tie with W[ef-1])
@@ -294,28 +340,38 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
         const uint32_t p = b0 + __ffs(mm) - 1;
         w.p_lo = p + 1;
         const uint32_t cur = w.row[p];
+        // the runner-up is the most likely next expansion: its adjacency line is fetched now (layer 0), so
+        // that the next expansion does not start with a dependent memory round trip
+        const uint32_t m2 = mm & (mm - 1);
+        const uint32_t row2 = (lc == 0 && m2) ? w.row[b0 + __ffs(m2) - 1] : ROW_NONE;
         __syncwarp();
         if (lane == 0) reinterpret_cast<uint32_t*>(w.key)[2 * p] |= 1u;
         __syncwarp();
         ++hops;
-        if ((int)a.levels[cur] < lc) continue;   // GetConnections(layer) is empty for good (hnsw.go:45-50)
+        if (lc > 0 && (int)a.levels[cur] < lc) continue;   // GetConnections(layer) is empty for good (hnsw.go:45-50)
         if (visited + stride > a.hash_size - (a.hash_size >> 3)) {
           overflow = true;
           break;
         }
         const uint32_t* list = (lc == 0) ? a.adj0 + (size_t)cur * a.s0 : a.adj_up + ((size_t)a.up_off[cur] + (lc - 1)) * a.su;
+        uint32_t nb_first = ROW_NONE;
+        if (lc == 0) {
+          nb_first = (cur == pre_row) ? pre_nb : ((lane < stride) ? __ldg(list + lane) : ROW_NONE);
+          pre_row = row2;
+          if (row2 != ROW_NONE) pre_nb = (lane < stride) ? __ldg(a.adj0 + (size_t)row2 * a.s0 + lane) : ROW_NONE;
+        }
         for (uint32_t c0 = 0; c0 < stride; c0 += 32) {
-          const uint32_t nb = (c0 + lane < stride) ? __ldg(list + c0 + lane) : ROW_NONE;
+          const uint32_t nb = (lc == 0 && c0 == 0) ? nb_first : ((c0 + lane < stride) ? __ldg(list + c0 + lane) : ROW_NONE);
           bool ok = (nb != ROW_NONE);
           const uint32_t listed = __ballot_sync(0xffffffffu, ok);
-          if (listed) gather_begin<GCH, 1>(a.vec, a.pitch, nb, listed, stage, lane);   // rows fly while the table is probed
+          if (listed) gather_all_begin<NB>(a.vec, a.pitch, nb, listed, stage, lane);   // rows fly while the table is probed
           if (ok && a.has_deleted) ok = !bit_test(a.deleted, nb);   // deleted: not marked visited, not traversed (hnsw.go:527-530)
           ok = visited_insert_warp(hash, n_groups, nb, ok, false, make_uint4(0, 0, 0, 0), lane, tag, row_bits);
           const uint32_t mask = __ballot_sync(0xffffffffu, ok);
           // threshold in force when this part of the list is examined (hnsw.go:536-542)
           const uint32_t worst = (w.cnt >= ef) ? reinterpret_cast<const uint32_t*>(w.key)[2 * (ef - 1) + 1] : LOG_NOT_FULL;
           float d = INF;
-          if (listed) d = gather_finish<METRIC, GCH, 1>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
+          if (listed) d = gather_all_finish<METRIC, NB>(a.vec, a.norm, a.pitch, sq, qn, nb, mask, stage, lane);
           visited += __popc(mask);
           evals += __popc(mask);
           const uint32_t od = f32_ord(d);
@@ -650,17 +706,34 @@ static int32_t ensure_graph_capacity(scn_store* s, BuildState* b, uint64_t rows,
   return SCN_OK;
 }
 
-template <int METRIC>
-static int32_t launch_build_search(const BuildArgs& a, bool long_rows, int grid, size_t smem, cudaStream_t st) {
-  if (long_rows) {
-    SCN_ALLOW_SMEM((hnsw_build_search_kernel<METRIC, 512>), smem);
-    hnsw_build_search_kernel<METRIC, 512><<<grid, 32, smem, st>>>(a);
-  } else {
-    SCN_ALLOW_SMEM((hnsw_build_search_kernel<METRIC, 256>), smem);
-    hnsw_build_search_kernel<METRIC, 256><<<grid, 32, smem, st>>>(a);
+// nb = resident 512-byte stages per row (1, 2, 4 or 6). `launch` = false: only sets the shared-memory
+// limit and reports how many walks fit an SM.
+template <int METRIC, uint32_t NB>
+static int32_t build_search_nb(const BuildArgs& a, int grid, size_t smem, cudaStream_t st, bool launch, int* per_sm) {
+  SCN_ALLOW_SMEM((hnsw_build_search_kernel<METRIC, NB>), smem);
+  if (!launch) {
+    SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, hnsw_build_search_kernel<METRIC, NB>, 32, smem));
+    return SCN_OK;
   }
+  hnsw_build_search_kernel<METRIC, NB><<<grid, 32, smem, st>>>(a);
   SCN_LAUNCHED();
   return SCN_OK;
+}
+template <int METRIC>
+static int32_t build_search_metric(const BuildArgs& a, uint32_t nb, int grid, size_t smem, cudaStream_t st, bool launch, int* per_sm) {
+  switch (nb) {
+    case 1: return build_search_nb<METRIC, 1>(a, grid, smem, st, launch, per_sm);
+    case 2: return build_search_nb<METRIC, 2>(a, grid, smem, st, launch, per_sm);
+    case 4: return build_search_nb<METRIC, 4>(a, grid, smem, st, launch, per_sm);
+    default: return build_search_nb<METRIC, 6>(a, grid, smem, st, launch, per_sm);
+  }
+}
+static int32_t build_search(int metric, const BuildArgs& a, uint32_t nb, int grid, size_t smem, cudaStream_t st, bool launch, int* per_sm) {
+  switch (metric) {
+    case M_L2: return build_search_metric<M_L2>(a, nb, grid, smem, st, launch, per_sm);
+    case M_COS: return build_search_metric<M_COS>(a, nb, grid, smem, st, launch, per_sm);
+    default: return build_search_metric<M_IP>(a, nb, grid, smem, st, launch, per_sm);
+  }
 }
 
 }  // namespace scn
@@ -728,33 +801,12 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
   SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   const uint32_t efc = (uint32_t)ef_construction;
   const uint32_t ef_pad = std::max(64u, round_up(2 * efc, 32));   // W + ghosts (see WState)
-  const bool long_rows = s->pitch * 4 > 512;
-  const size_t smem = build_warp_bytes(s->pitch, ef_pad, ga_stage_bytes(long_rows ? 512 : 256, 1));
+  const uint32_t n_chunks = (s->pitch * 4 + 511) / 512;
+  const uint32_t nb = n_chunks <= 1 ? 1u : n_chunks <= 2 ? 2u : n_chunks <= 4 ? 4u : 6u;   // resident stages per row
+  const size_t smem = build_warp_bytes(s->pitch, ef_pad, ga_stage_bytes(512, nb));
   if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "efConstruction=%u / dim=%u need more shared memory than one SM has", efc, s->dim);
   int per_sm = 0;
-  {
-    cudaError_t e;
-#define OCC(MT)                                                                                                            \
-  e = long_rows ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_build_search_kernel<MT, 512>, 32, smem)     \
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hnsw_build_search_kernel<MT, 256>, 32, smem)
-    // (the opt-in shared-memory limit must be set before the occupancy query)
-    switch (s->metric) {
-      case M_L2:
-        if (long_rows) SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_L2, 512>), smem); else SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_L2, 256>), smem);
-        OCC(M_L2);
-        break;
-      case M_COS:
-        if (long_rows) SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_COS, 512>), smem); else SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_COS, 256>), smem);
-        OCC(M_COS);
-        break;
-      default:
-        if (long_rows) SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_IP, 512>), smem); else SCN_ALLOW_SMEM((hnsw_build_search_kernel<M_IP, 256>), smem);
-        OCC(M_IP);
-        break;
-    }
-#undef OCC
-    SCN_CUDA(e);
-  }
+  SCN_TRY(build_search(s->metric, BuildArgs{}, nb, 0, smem, st, false, &per_sm));
   if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "the build search kernel does not fit an SM");
   const uint32_t max_window = (uint32_t)std::min<uint64_t>((uint64_t)sms * per_sm, 2048);   // one wave of walks
   // visited table per resident walk: ~2M*1.25 rows per expansion, ~1.5 efc expansions, under 7/8 full
@@ -846,7 +898,9 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
       continue;
     }
     // ---- window of the next inserts, all searched against the graph as it is now ---------------------
-    uint32_t want = (uint32_t)std::min<double>(max_window, 2.0 * avg_commits + 8.0);
+    // a round lasts as long as its slowest walk (a level-L node runs L + 1 searches): speculate about as far
+    // as the rounds have been getting, not much further
+    uint32_t want = (uint32_t)std::min<double>(max_window, 1.5 * avg_commits + 4.0);
     if (s->opt_build_window > 0) want = (uint32_t)std::min<int64_t>(s->opt_build_window, max_window);   // 1 = no speculation at all
     uint32_t W = (uint32_t)std::min<uint64_t>(want, n - done);
     uint32_t n_lists = 0;
@@ -905,13 +959,7 @@ int32_t scn_hnsw_insert(scn_store* s, uint64_t n, const int32_t* levels, int32_t
     a.log = d_log;
     a.log_cnt = d_logcnt;
     a.stats = s->d_counters;
-    int32_t rc;
-    switch (s->metric) {
-      case M_L2: rc = launch_build_search<M_L2>(a, long_rows, (int)W, smem, st); break;
-      case M_COS: rc = launch_build_search<M_COS>(a, long_rows, (int)W, smem, st); break;
-      default: rc = launch_build_search<M_IP>(a, long_rows, (int)W, smem, st); break;
-    }
-    SCN_TRY(rc);
+    SCN_TRY(build_search(s->metric, a, nb, (int)W, smem, st, true, nullptr));
     const uint32_t P = std::min(W, pair_cap);
     if (P > 1) {
       switch (s->metric) {
