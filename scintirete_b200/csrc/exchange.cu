@@ -285,25 +285,48 @@ int32_t scn_exchange_slice(const scn_exchange* ex, uint64_t nq, uint32_t rank, u
   return SCN_OK;
 }
 
-int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, int32_t q_is_slice, uint64_t nq, uint32_t k,
-                                     uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
-                                     void* stream) {
+}  // extern "C"
+
+// One rank's call, cut at the points where it starts to wait for its peers. Ranks that share a DEVICE
+// (tests, smoke: several shards of one process on one GPU) must not launch a wait before every rank
+// has finished ENQUEUEING what that wait depends on — a host-side allocation of a peer can block behind
+// a spinning wait kernel on the same device — so a driver of such ranks runs the three steps with a
+// host barrier between them (shards.cu). With one rank per device the steps simply follow each other.
+namespace scn {
+
+struct ExchangeCall {
+  scn_store* s;
+  scn_exchange* ex;
+  cudaStream_t st;
+  Profiler prof;
+  Scratch scratch;
+  PeerArgs a;
+  const float* d_q_full = nullptr;
+  uint64_t* d_keys = nullptr;
+  uint64_t nq = 0, q_lo = 0, q_n = 0, row_base = 0;
+  uint32_t k = 0, per = 0;
+  bool q_is_slice = false;
+  ExchangeCall(scn_store* s_, scn_exchange* ex_, cudaStream_t st_) : s(s_), ex(ex_), st(st_), prof(s_, st_), scratch(st_) {}
+};
+
+// step 1: argument checks, this rank's query slice -> every rank's query buffer
+int32_t exchange_begin(ExchangeCall& c, const float* d_q, int32_t q_is_slice, uint64_t nq, uint32_t k, uint64_t row_base) {
+  scn_store* s = c.s;
+  scn_exchange* ex = c.ex;
   if (!s || !ex) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
   if (!ex->connected) return fail(SCN_ERR_INVALID_PARAMETERS, "exchange is not connected to its peers");
   if (s->device != ex->device) return fail(SCN_ERR_INVALID_PARAMETERS, "store and exchange live on different devices");
   if (k != ex->k || nq == 0 || nq > ex->max_nq) return fail(SCN_ERR_INVALID_PARAMETERS, "nq must be in [1, %llu] and k == %u", (unsigned long long)ex->max_nq, ex->k);
   if (q_is_slice && ex->dim != s->dim) return fail(SCN_ERR_INVALID_PARAMETERS, "the exchange was created for dim %u, the store has %u", ex->dim, s->dim);
   if (row_base + s->rows >= (uint64_t)ROW_NONE) return fail(SCN_ERR_INVALID_PARAMETERS, "global row index exceeds 32 bits");
-  DeviceGuard g(s->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  uint64_t q_lo = 0, q_n = 0;
-  scn_exchange_slice(ex, nq, ex->rank, &q_lo, &q_n);
-  if ((q_n && !d_q && q_is_slice) || (!q_is_slice && !d_q)) return fail(SCN_ERR_INVALID_PARAMETERS, "query pointer is NULL");
-  if (q_n && (!d_out_ids || !d_out_dist)) return fail(SCN_ERR_INVALID_PARAMETERS, "output pointer is NULL");
-  Profiler prof(s, st);
-  Scratch scratch(st);
+  scn_exchange_slice(ex, nq, ex->rank, &c.q_lo, &c.q_n);
+  if ((c.q_n && !d_q && q_is_slice) || (!q_is_slice && !d_q)) return fail(SCN_ERR_INVALID_PARAMETERS, "query pointer is NULL");
+  c.nq = nq;
+  c.k = k;
+  c.row_base = row_base;
+  c.q_is_slice = q_is_slice != 0;
   const uint64_t epoch = ++ex->epoch;
-  PeerArgs a;
+  PeerArgs& a = c.a;
   for (int r = 0; r < 16; ++r) a.peer[r] = ex->peer[r];
   a.L.world = ex->world;
   a.L.le = (size_t)ex->slice_cap * k;
@@ -311,50 +334,150 @@ int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float
   a.rank = ex->rank;
   a.parity = (uint32_t)(epoch & 1);
   a.epoch = epoch_value(epoch);
-  const uint32_t per = (uint32_t)((nq + ex->world - 1) / ex->world);
-
-  // ---- 1. query gather over NVLink --------------------------------------------------------------
-  const float* d_q_full = d_q;
-  if (q_is_slice) {
-    prof.begin("scatter_queries");
+  c.per = (uint32_t)((nq + ex->world - 1) / ex->world);
+  c.d_q_full = d_q;
+  SCN_TRY(c.scratch.alloc(&c.d_keys, nq * k));   // (allocated here: nothing is allocated once a rank may be waiting)
+  if (c.q_is_slice) {
+    c.prof.begin("scatter_queries");
     a.done = ex->d_done + 1;
-    const uint64_t n_floats = q_n * s->dim;
+    const uint64_t n_floats = c.q_n * s->dim;
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(148, (n_floats / 4 + 255) / 256));
-    scatter_queries_kernel<<<blocks, 256, 0, st>>>(a, d_q, n_floats, q_lo * s->dim);
+    scatter_queries_kernel<<<blocks, 256, 0, c.st>>>(a, d_q, n_floats, c.q_lo * s->dim);
     SCN_LAUNCHED();
-    wait_flags_kernel<<<1, 32, 0, st>>>(flag_of(ex->local, FLAG_QUERIES, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
-    SCN_LAUNCHED();
-    prof.end();
-    d_q_full = queries_of(ex->local, a.L, a.parity);
+    c.prof.end();
+    c.d_q_full = queries_of(ex->local, a.L, a.parity);
   }
-
-  // ---- 2. shard-local search of the whole batch ---------------------------------------------------
-  uint64_t* d_keys = nullptr;
-  SCN_TRY(scratch.alloc(&d_keys, nq * k));
-  SCN_TRY(flat_keys(s, d_q_full, nq, k, row_base, d_keys, st, &prof));
-
-  // ---- 3. push each list to the owner of its query's slice -----------------------------------------
-  a.done = ex->d_done;
-  prof.begin("push_results");
-  const uint64_t n = nq * k;
-  const unsigned blocks = (unsigned)std::min<uint64_t>(148, (n / 2 + 255) / 256 + 1);
-  push_results_kernel<<<blocks, 256, 0, st>>>(a, d_keys, s->d_ids, n, k, per, (uint32_t)row_base);
-  SCN_LAUNCHED();
-  prof.end();
-
-  // ---- 4. wait for the peers, merge this rank's slice from local memory -----------------------------
-  prof.begin("wait_peers");
-  wait_flags_kernel<<<1, 32, 0, st>>>(flag_of(ex->local, FLAG_LISTS, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
-  SCN_LAUNCHED();
-  prof.end();
-  if (q_n) {
-    prof.begin("merge_topk");
-    SCN_TRY(merge_topk(keys_of(ex->local, a.L, a.parity, 0), ids_of(ex->local, a.L, a.parity, 0), ex->world, q_n, k, d_out_ids, d_out_dist,
-                       d_out_counts, st, a.L.le, ex->d_status));
-    prof.end();
-  }
-  prof.collect();
   return SCN_OK;
+}
+
+// step 2: (wait for the query slices,) shard-local search of the whole batch, push each list to the
+// owner of its query's slice
+int32_t exchange_search(ExchangeCall& c) {
+  scn_store* s = c.s;
+  scn_exchange* ex = c.ex;
+  PeerArgs& a = c.a;
+  if (c.q_is_slice) {
+    c.prof.begin("wait_queries");
+    wait_flags_kernel<<<1, 32, 0, c.st>>>(flag_of(ex->local, FLAG_QUERIES, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
+    SCN_LAUNCHED();
+    c.prof.end();
+  }
+  SCN_TRY(flat_keys(s, c.d_q_full, c.nq, c.k, c.row_base, c.d_keys, c.st, &c.prof));
+  a.done = ex->d_done;
+  c.prof.begin("push_results");
+  const uint64_t n = c.nq * c.k;
+  const unsigned blocks = (unsigned)std::min<uint64_t>(148, (n / 2 + 255) / 256 + 1);
+  push_results_kernel<<<blocks, 256, 0, c.st>>>(a, c.d_keys, s->d_ids, n, c.k, c.per, (uint32_t)c.row_base);
+  SCN_LAUNCHED();
+  c.prof.end();
+  return SCN_OK;
+}
+
+// step 3: wait for the peers' lists, merge this rank's slice from local memory
+int32_t exchange_finish(ExchangeCall& c, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts) {
+  scn_exchange* ex = c.ex;
+  PeerArgs& a = c.a;
+  if (c.q_n && (!d_out_ids || !d_out_dist)) return fail(SCN_ERR_INVALID_PARAMETERS, "output pointer is NULL");
+  c.prof.begin("wait_peers");
+  wait_flags_kernel<<<1, 32, 0, c.st>>>(flag_of(ex->local, FLAG_LISTS, a.parity, 0), ex->world, a.epoch, ex->d_status, WAIT_TIMEOUT_NS);
+  SCN_LAUNCHED();
+  c.prof.end();
+  if (c.q_n) {
+    c.prof.begin("merge_topk");
+    SCN_TRY(merge_topk(keys_of(ex->local, a.L, a.parity, 0), ids_of(ex->local, a.L, a.parity, 0), ex->world, c.q_n, c.k, d_out_ids,
+                       d_out_dist, d_out_counts, c.st, a.L.le, ex->d_status));
+    c.prof.end();
+  }
+  c.prof.collect();
+  return SCN_OK;
+}
+
+// Host-buffer form in the same three steps (shards.cu drives them): the per-call device buffers live in `h`.
+struct HostExchangeCall {
+  ExchangeCall call;
+  float* d_q = nullptr;
+  uint64_t* d_ids = nullptr;
+  float* d_dist = nullptr;
+  uint32_t* d_counts = nullptr;
+  HostExchangeCall(scn_store* s, scn_exchange* ex, cudaStream_t st) : call(s, ex, st) {}
+};
+
+HostExchangeCall* host_exchange_begin(scn_store* s, scn_exchange* ex, const float* q_slice, uint64_t nq, uint32_t k, uint64_t row_base,
+                                      int32_t* rc) {
+  *rc = SCN_OK;
+  if (!s || !ex) {
+    *rc = fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+    return nullptr;
+  }
+  if (ex->dim != s->dim) {
+    *rc = fail(SCN_ERR_INVALID_PARAMETERS, "the exchange was created for dim %u, the store has %u", ex->dim, s->dim);
+    return nullptr;
+  }
+  DeviceGuard g(s->device);
+  HostExchangeCall* h = new HostExchangeCall(s, ex, thread_stream(s->device));
+  uint64_t q_lo = 0, q_n = 0;
+  scn_exchange_slice(ex, nq, ex->rank, &q_lo, &q_n);
+  auto bail = [&](int32_t r) -> HostExchangeCall* {
+    *rc = r;
+    delete h;
+    return nullptr;
+  };
+  if (q_n && !q_slice) return bail(fail(SCN_ERR_INVALID_PARAMETERS, "query pointer is NULL"));
+  const uint64_t m = std::max<uint64_t>(q_n, 1);
+  int32_t r = h->call.scratch.alloc(&h->d_q, m * s->dim);
+  if (r == SCN_OK) r = h->call.scratch.alloc(&h->d_ids, m * k);
+  if (r == SCN_OK) r = h->call.scratch.alloc(&h->d_dist, m * k);
+  if (r == SCN_OK) r = h->call.scratch.alloc(&h->d_counts, m);
+  if (r == SCN_OK && q_n) r = copy_to_device(h->d_q, q_slice, q_n * s->dim * sizeof(float), h->call.st);
+  if (r == SCN_OK) r = exchange_begin(h->call, h->d_q, 1, nq, k, row_base);
+  if (r != SCN_OK) return bail(r);
+  return h;
+}
+
+int32_t host_exchange_search(HostExchangeCall* h) {
+  DeviceGuard g(h->call.s->device);
+  return exchange_search(h->call);
+}
+
+// consumes h
+int32_t host_exchange_finish(HostExchangeCall* h, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+  DeviceGuard g(h->call.s->device);
+  const uint64_t q_n = h->call.q_n;
+  const uint32_t k = h->call.k;
+  cudaStream_t st = h->call.st;
+  scn_exchange* ex = h->call.ex;
+  int32_t rc = (q_n && (!out_ids || !out_dist)) ? fail(SCN_ERR_INVALID_PARAMETERS, "output pointer is NULL") : SCN_OK;
+  if (rc == SCN_OK) rc = exchange_finish(h->call, h->d_ids, h->d_dist, h->d_counts);
+  if (rc == SCN_OK && q_n) {
+    cudaError_t e = cudaMemcpyAsync(out_ids, h->d_ids, q_n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, h->d_dist, q_n * k * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_counts) e = cudaMemcpyAsync(out_counts, h->d_counts, q_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "result copy", __FILE__, __LINE__);
+  }
+  const int32_t st_rc = scn_exchange_status(ex, st);   // synchronises the stream
+  delete h;
+  return rc != SCN_OK ? rc : st_rc;
+}
+
+void host_exchange_abort(HostExchangeCall* h) {
+  if (!h) return;
+  cudaStreamSynchronize(h->call.st);
+  delete h;
+}
+
+}  // namespace scn
+
+extern "C" {
+
+int32_t scn_search_flat_exchange_dev(scn_store* s, scn_exchange* ex, const float* d_q, int32_t q_is_slice, uint64_t nq, uint32_t k,
+                                     uint64_t row_base, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                                     void* stream) {
+  if (!s || !ex) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
+  DeviceGuard g(s->device);
+  ExchangeCall c(s, ex, (cudaStream_t)stream);
+  SCN_TRY(exchange_begin(c, d_q, q_is_slice, nq, k, row_base));
+  SCN_TRY(exchange_search(c));
+  return exchange_finish(c, d_out_ids, d_out_dist, d_out_counts);
 }
 
 // Synchronises `stream`; SCN_ERR_SEARCH_FAILED if a peer missed the 5 s arrival time-out since the
@@ -376,30 +499,15 @@ int32_t scn_exchange_status(scn_exchange* ex, void* stream) {
 // scn_exchange_slice(ex, nq, rank)), the outputs receive the results of that slice. Blocking.
 int32_t scn_search_flat_exchange(scn_store* s, scn_exchange* ex, const float* q_slice, uint64_t nq, uint32_t k, uint64_t row_base,
                                  uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
-  if (!s || !ex) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
-  if (ex->dim != s->dim) return fail(SCN_ERR_INVALID_PARAMETERS, "the exchange was created for dim %u, the store has %u", ex->dim, s->dim);
-  uint64_t q_lo = 0, q_n = 0;
-  SCN_TRY(scn_exchange_slice(ex, nq, ex->rank, &q_lo, &q_n));
-  if (q_n && (!q_slice || !out_ids || !out_dist)) return fail(SCN_ERR_INVALID_PARAMETERS, "NULL argument");
-  DeviceGuard g(s->device);
-  cudaStream_t st = thread_stream(s->device);
-  Scratch scratch(st);
-  float* d_q = nullptr;
-  uint64_t* d_ids = nullptr;
-  float* d_dist = nullptr;
-  uint32_t* d_counts = nullptr;
-  SCN_TRY(scratch.alloc(&d_q, std::max<uint64_t>(q_n, 1) * s->dim));
-  SCN_TRY(scratch.alloc(&d_ids, std::max<uint64_t>(q_n, 1) * k));
-  SCN_TRY(scratch.alloc(&d_dist, std::max<uint64_t>(q_n, 1) * k));
-  SCN_TRY(scratch.alloc(&d_counts, std::max<uint64_t>(q_n, 1)));
-  if (q_n) SCN_TRY(copy_to_device(d_q, q_slice, q_n * s->dim * sizeof(float), st));
-  SCN_TRY(scn_search_flat_exchange_dev(s, ex, d_q, 1, nq, k, row_base, d_ids, d_dist, d_counts, st));
-  if (q_n) {
-    SCN_CUDA(cudaMemcpyAsync(out_ids, d_ids, q_n * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    SCN_CUDA(cudaMemcpyAsync(out_dist, d_dist, q_n * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out_counts) SCN_CUDA(cudaMemcpyAsync(out_counts, d_counts, q_n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  int32_t rc = SCN_OK;
+  HostExchangeCall* h = host_exchange_begin(s, ex, q_slice, nq, k, row_base, &rc);
+  if (!h) return rc;
+  rc = host_exchange_search(h);
+  if (rc != SCN_OK) {
+    host_exchange_abort(h);
+    return rc;
   }
-  return scn_exchange_status(ex, st);
+  return host_exchange_finish(h, out_ids, out_dist, out_counts);
 }
 
 }  // extern "C"

@@ -103,6 +103,7 @@ struct scn_shards {
   uint64_t ex_max_nq = 0;
   uint32_t ex_k = 0;
   std::mutex mu;  // one sharded search at a time (a collective over all devices)
+  bool shared_device = false;  // two shards on one GPU (tests): the exchange runs in host-synchronised steps
 
   uint64_t row_base(uint32_t g) const { return (uint64_t)g * per; }
 };
@@ -173,6 +174,8 @@ int32_t scn_shards_create(const int32_t* devices, int32_t ndev, uint32_t dim, in
   sh->capacity = std::max<uint64_t>(capacity_rows, 1);
   sh->per = (sh->capacity + sh->world - 1) / sh->world;
   sh->devices.assign(devices, devices + ndev);
+  for (int a = 0; a < ndev; ++a)
+    for (int c = a + 1; c < ndev; ++c) sh->shared_device |= devices[a] == devices[c];
   for (int g = 0; g < ndev; ++g) {
     scn_store* s = nullptr;
     const int32_t rc = scn_store_create(devices[g], dim, metric, &s);
@@ -305,11 +308,38 @@ int32_t scn_shards_search_flat(scn_shards* sh, const float* q, uint64_t nq, uint
   if (nq == 0) return SCN_OK;
   std::lock_guard<std::mutex> lk(sh->mu);
   SCN_TRY(ensure_exchanges(sh, nq, k));
+  if (!sh->shared_device)
+    return run_all(sh, [&](uint32_t g) -> int32_t {
+      uint64_t lo = 0, cnt = 0;
+      SCN_TRY(scn_exchange_slice(sh->ex[g], nq, g, &lo, &cnt));
+      return scn_search_flat_exchange(sh->stores[g], sh->ex[g], q + lo * sh->dim, nq, k, sh->row_base(g), out_ids + lo * k,
+                                      out_dist + lo * k, out_counts ? out_counts + lo : nullptr);
+    });
+  // Shards that share a GPU: no rank may start waiting for its peers before every rank has finished
+  // enqueueing what the wait depends on (a peer's host-side allocation can block behind a spinning
+  // wait kernel on the same device) — a host barrier after each of the three steps.
+  std::vector<HostExchangeCall*> calls(sh->world, nullptr);
+  int32_t rc = run_all(sh, [&](uint32_t g) -> int32_t {
+    uint64_t lo = 0, cnt = 0;
+    SCN_TRY(scn_exchange_slice(sh->ex[g], nq, g, &lo, &cnt));
+    int32_t r = SCN_OK;
+    calls[g] = host_exchange_begin(sh->stores[g], sh->ex[g], q + lo * sh->dim, nq, k, sh->row_base(g), &r);
+    return r;
+  });
+  if (rc == SCN_OK) rc = run_all(sh, [&](uint32_t g) -> int32_t { return host_exchange_search(calls[g]); });
+  if (rc != SCN_OK) {
+    std::string msg = scn_last_error();
+    run_all(sh, [&](uint32_t g) -> int32_t {
+      host_exchange_abort(calls[g]);
+      return SCN_OK;
+    });
+    drop_exchanges(sh);   // the ranks are out of step: start over with fresh buffers next time
+    return fail(rc, "%s", msg.c_str());
+  }
   return run_all(sh, [&](uint32_t g) -> int32_t {
     uint64_t lo = 0, cnt = 0;
     SCN_TRY(scn_exchange_slice(sh->ex[g], nq, g, &lo, &cnt));
-    return scn_search_flat_exchange(sh->stores[g], sh->ex[g], q + lo * sh->dim, nq, k, sh->row_base(g), out_ids + lo * k,
-                                    out_dist + lo * k, out_counts ? out_counts + lo : nullptr);
+    return host_exchange_finish(calls[g], out_ids + lo * k, out_dist + lo * k, out_counts ? out_counts + lo : nullptr);
   });
 }
 

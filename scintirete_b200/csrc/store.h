@@ -169,6 +169,15 @@ struct Profiler {
 };
 
 void free_build_state(scn_store* s);
+
+// One rank's host-buffer call of the fused shard exchange in three steps (exchange.cu); shards.cu puts a
+// host barrier between them when several shards share a device.
+struct HostExchangeCall;
+HostExchangeCall* host_exchange_begin(scn_store* s, scn_exchange* ex, const float* q_slice, uint64_t nq, uint32_t k, uint64_t row_base,
+                                      int32_t* rc);
+int32_t host_exchange_search(HostExchangeCall* h);
+int32_t host_exchange_finish(HostExchangeCall* h, uint64_t* out_ids, float* out_dist, uint32_t* out_counts);   // consumes h
+void host_exchange_abort(HostExchangeCall* h);
 cudaStream_t thread_stream(int device);
 // Host -> device copy of a caller's buffer, enqueued on `stream`. Pinned / registered memory is
 // copied directly; pageable memory (a Go slice, a numpy array) goes through two pinned staging
