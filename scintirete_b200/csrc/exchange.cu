@@ -288,10 +288,11 @@ int32_t scn_exchange_slice(const scn_exchange* ex, uint64_t nq, uint32_t rank, u
 }  // extern "C"
 
 // One rank's call, cut at the points where it starts to wait for its peers. Ranks that share a DEVICE
-// (tests, smoke: several shards of one process on one GPU) must not launch a wait before every rank
-// has finished ENQUEUEING what that wait depends on — a host-side allocation of a peer can block behind
-// a spinning wait kernel on the same device — so a driver of such ranks runs the three steps with a
-// host barrier between them (shards.cu). With one rank per device the steps simply follow each other.
+// (tests, smoke: several shards of one process on one GPU) must never have a kernel spinning on a flag
+// that another launch on the same GPU is to raise — nothing guarantees that two launches run at the
+// same time — so a driver of such ranks runs the three steps with a host barrier AND a stream
+// synchronisation between them (shards.cu): every wait kernel then finds its flags already raised.
+// With one rank per device the steps simply follow each other.
 namespace scn {
 
 struct ExchangeCall {
@@ -457,6 +458,13 @@ int32_t host_exchange_finish(HostExchangeCall* h, uint64_t* out_ids, float* out_
   const int32_t st_rc = scn_exchange_status(ex, st);   // synchronises the stream
   delete h;
   return rc != SCN_OK ? rc : st_rc;
+}
+
+// everything this rank has enqueued so far has run (shards sharing a device: see shards.cu)
+int32_t host_exchange_sync(HostExchangeCall* h) {
+  DeviceGuard g(h->call.s->device);
+  SCN_CUDA(cudaStreamSynchronize(h->call.st));
+  return SCN_OK;
 }
 
 void host_exchange_abort(HostExchangeCall* h) {

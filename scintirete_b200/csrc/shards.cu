@@ -315,18 +315,22 @@ int32_t scn_shards_search_flat(scn_shards* sh, const float* q, uint64_t nq, uint
       return scn_search_flat_exchange(sh->stores[g], sh->ex[g], q + lo * sh->dim, nq, k, sh->row_base(g), out_ids + lo * k,
                                       out_dist + lo * k, out_counts ? out_counts + lo : nullptr);
     });
-  // Shards that share a GPU: no rank may start waiting for its peers before every rank has finished
-  // enqueueing what the wait depends on (a peer's host-side allocation can block behind a spinning
-  // wait kernel on the same device) — a host barrier after each of the three steps.
+  // Shards that share a GPU: a kernel must never spin on a flag that another launch on the same GPU
+  // is to raise (nothing guarantees that the two run at the same time). Each of the three steps ends
+  // with a stream synchronisation and a host barrier, so every wait kernel finds its flags raised.
   std::vector<HostExchangeCall*> calls(sh->world, nullptr);
   int32_t rc = run_all(sh, [&](uint32_t g) -> int32_t {
     uint64_t lo = 0, cnt = 0;
     SCN_TRY(scn_exchange_slice(sh->ex[g], nq, g, &lo, &cnt));
     int32_t r = SCN_OK;
     calls[g] = host_exchange_begin(sh->stores[g], sh->ex[g], q + lo * sh->dim, nq, k, sh->row_base(g), &r);
-    return r;
+    return r != SCN_OK ? r : host_exchange_sync(calls[g]);
   });
-  if (rc == SCN_OK) rc = run_all(sh, [&](uint32_t g) -> int32_t { return host_exchange_search(calls[g]); });
+  if (rc == SCN_OK)
+    rc = run_all(sh, [&](uint32_t g) -> int32_t {
+      SCN_TRY(host_exchange_search(calls[g]));
+      return host_exchange_sync(calls[g]);
+    });
   if (rc != SCN_OK) {
     std::string msg = scn_last_error();
     run_all(sh, [&](uint32_t g) -> int32_t {

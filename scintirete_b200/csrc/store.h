@@ -177,6 +177,7 @@ HostExchangeCall* host_exchange_begin(scn_store* s, scn_exchange* ex, const floa
                                       int32_t* rc);
 int32_t host_exchange_search(HostExchangeCall* h);
 int32_t host_exchange_finish(HostExchangeCall* h, uint64_t* out_ids, float* out_dist, uint32_t* out_counts);   // consumes h
+int32_t host_exchange_sync(HostExchangeCall* h);
 void host_exchange_abort(HostExchangeCall* h);
 cudaStream_t thread_stream(int device);
 // Host -> device copy of a caller's buffer, enqueued on `stream`. Pinned / registered memory is

@@ -3,9 +3,9 @@ import sys
 
 import pytest
 
-# Several tests drive G "ranks" of the fused shard exchange on ONE GPU, each on its own stream, and a
-# rank's wait kernel spins until the other ranks' kernels have run: give every stream its own
-# hardware queue so that no rank is queued behind another rank's wait (must be set before CUDA starts).
+# The shard-set tests run several shards of one process on one GPU, one worker thread and stream each:
+# give every stream its own hardware queue (must be set before CUDA starts). Kernels never wait on one
+# another there — the steps of the exchange are synchronised on the host when shards share a device.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
