@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from scintirete_b200 import DistanceMetric, GPUHNSWIndex, GraphState, HNSWParams, ScintireteError, SearchParams
+from scintirete_b200 import DistanceMetric, GPUHNSWIndex, GraphState, HNSWParams, ScintireteError, SearchParams, Vector
 from util import gaussian, recall, to_graph_state
 
 pytestmark = pytest.mark.gpu
@@ -100,8 +100,13 @@ def test_empty_and_single_and_toy_graphs():
     res = g2.search([0.0, 0.0], SearchParams(top_k=2))                                      # hnsw_test.go:124-160
     o = h.search([0.0, 0.0], 2)
     assert [r.vector.id for r in res] == list(o[0]) and [np.float32(r.distance) for r in res] == list(o[1])
-    with pytest.raises(ScintireteError):
-        g2.build([])
+    g2.build([])                                                                            # Build clears first (hnsw.go:148-156)
+    assert g2.size() == 0 and len(g2.search([0.0, 0.0], SearchParams(top_k=2))) == 0
+    # Build on the device: the same toy vectors, linked by scn_hnsw_insert with the oracle's level draws
+    st = h.export_graph_state()
+    g2.build([Vector(i + 1, v) for i, v in enumerate(st.vectors)], levels=st.list_counts - 1)
+    res = g2.search([0.0, 0.0], SearchParams(top_k=2))
+    assert [r.vector.id for r in res] == list(o[0]) and [np.float32(r.distance) for r in res] == list(o[1])
 
 
 def test_visited_overflow_path_gives_same_answer():
