@@ -331,6 +331,8 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "overfetch"         candidates kept per query and column block by the tensor filter (0 = auto)
  *   "tensor_hint"       1 = lists of a query start from the threshold of the finished ones (default)
  *   "tensor_bn"         128 forces 128-row tiles (0 = auto); "tensor_chunks" row chunks per query block (0 = auto)
+ *   "tensor_pair"       1 = CTA-pair filter kernel (tcgen05 cta_group::2) for 448 < dim <= 512 and 576 < dim <= 768 at
+ *                       batches of >= 256 queries (default), 0 = the single-CTA kernel everywhere
  *   "hnsw_gather"       row gather of hnsw_search: -1 auto, 0 registers (LDG.256), 1 / 2 / 3 shared-memory
  *                       stages of 512 B / 2 x 512 B / 256 B; "hnsw_gather_long" the auto choice for rows > 512 B
  *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory

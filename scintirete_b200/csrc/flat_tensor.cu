@@ -20,6 +20,9 @@
 // wave of query blocks (L2 keeps the tile window shared by the CTAs that walk the same chunk).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "store.h"
 
 namespace scn {
@@ -506,25 +509,28 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
 }
 
 // ================================================================================================
-// tensor_filter2_kernel — the same filter on CTA PAIRS (tcgen05 cta_group::2), for long rows and
-// large batches. The TMEM-stationary kernel above is bound by its MMA shape: next to a 384-column A
-// operand only N = 64 fits twice, and a 128 x 64 x 16 instruction is too short to hide its issue
-// overhead (tensor pipe 62 % active at D = 768). Here two CTAs of one cluster (one TPC) work on one
-// 256-query x 256-row tile: both operands are streamed by TMA in 64-K stages (each CTA loads the A
-// block of ITS 128 queries and ITS 128 rows of the B tile), ONE lane of the leader CTA issues
-// tcgen05.mma.cta_group::2 M = 256 N = 256 K = 16 — four 128-cycle instructions per stage — and each
-// CTA finds the scores of its 128 queries against all 256 rows in its own TMEM (two 256-column
-// accumulators = all 512 columns, so the next tile is computed while this one is gated). L2 -> SM
-// traffic per MMA flop equals the stationary kernel's (64 MAC per byte).
+// tensor_filter2_kernel — the same filter on CTA PAIRS (tcgen05 cta_group::2), for kpad in {512, 640, 768}.
+// Measured with tools/ubench/mma_rate.cu: an M=128 N=64 K=16 instruction takes 44.6 cycles (72 % of the
+// tensor rate), N=128 takes exactly 64 (100 %). Next to the 384-column A operand a single CTA has room
+// for two 64-column accumulators or one of 128 columns, and with N = 128 it would have to pull 64 B/clk
+// of rows out of L2, more than one SM gets. A pair of CTAs (one cluster, one TPC) removes both limits:
+// each CTA keeps ITS 128 queries stationary in its own TMEM and loads only HALF of every 128-row tile
+// (64 rows per stage, 32 B/clk at full rate); one lane of the leader CTA issues
+// tcgen05.mma.cta_group::2 M=256 N=128 K=16 — 64 cycles on both SMs, each reading the other's rows
+// inside the TPC — and each CTA finds the scores of its 128 queries against all 128 rows in its own
+// 128-column accumulator.
 //   barriers   full[s]      leader CTA only; both CTAs' TMA transactions and one arrive each land here
 //              empty[s]     one per CTA; the MMA commit is multicast to both
-//              acc_full[b]  one per CTA; multicast commit after the last K stage of a tile
-//              acc_empty[b] leader CTA only; the 4 epilogue warps of BOTH CTAs arrive there
-// The epilogue is the one above (threshold gate, k' best per query and chunk in registers / smem),
-// fed 128 columns at a time.
-constexpr int TF2_STAGES = 5;                              // 32 KB each: A 128 x 64 + B 128 x 64 bf16
-constexpr int TF2_STAGE_BYTES = 2 * TF_BM * TF_BK * 2;
-constexpr int TF2_BN = 256;                                // rows per tile (UMMA N); 128 loaded per CTA
+//              acc_full     one per CTA; multicast commit after the last K stage of a tile
+//              acc_empty    leader CTA only; the 4 epilogue warps of BOTH CTAs arrive there once the
+//                           accumulator is in their registers (one accumulator: the next tile's MMAs
+//                           wait for this, ~15 % of a tile; the gate itself overlaps the next tile)
+//              a_ready      leader CTA only; both CTAs' epilogue warps arrive after storing A
+// The epilogue is the one above (threshold gate, k' best per query and chunk).
+constexpr int TF2_STAGES = 10;                             // 16 KB each: 64 rows x 128 K bf16 (two 64-K boxes)
+constexpr int TF2_STAGE_BYTES = 64 * 128 * 2;
+constexpr int TF2_BN = 128;                                // rows per pair tile (UMMA N); 64 loaded per CTA
+constexpr int TF2_KSTEP = 128;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -540,19 +546,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// (default semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU and `.acquire.cluster` on the
+// waiting side to CCTL.IVALL — an L1 flush per barrier round trip, measured at 40 % of the kernel. What the
+// barriers order here is TMEM / async-proxy traffic, which tcgen05.fence and tcgen05.commit cover.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAITC_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONEC_%=;\n\t"
-      "bra WAITC_%=;\n\t"
-      "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load whose completion is signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -567,35 +565,38 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {   // arrives on 
                "h"((uint16_t)3)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T on both SMs of the pair: M = 256 (128 TMEM lanes per CTA), B split by rows
+__device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
-template <int KP>
+// NBUF: accumulators per CTA — 2 when the A operand leaves room (kpad <= 512), else 1
+template <int KP, int NBUF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-    tensor_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a, FilterArgs a) {
+    tensor_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int ET = 128;                                                  // epilogue threads per CTA
   uint32_t* s_crow = reinterpret_cast<uint32_t*>(sb + TF2_STAGES * TF2_STAGE_BYTES);
   float* s_qs = reinterpret_cast<float*>(s_crow + ET * KP);                // [16][ET] queued scores
   uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * ET);            // [16][ET] queued columns
-  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);                 // [4 warps][2 buffers][256]
+  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);                 // [4 warps][2 buffers][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 4 * 2 * TF2_BN);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = full + TF2_STAGES;         // [STAGES]
   uint64_t* acc_full = empty + TF2_STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_ready = acc_empty + 2;           // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();     // 0 = leader (issues the MMAs)
-  const uint32_t KB = a.kpad / TF_BK;          // stages per tile
+  const uint32_t KB = a.kpad / TF2_KSTEP;      // stages per tile
   const uint32_t n_pairs = (a.n_qblocks + 1) / 2;
   const uint32_t n_items = n_pairs * a.n_chunks;
   const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -609,6 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       mbar_init(acc_full + i, 1);
       mbar_init(acc_empty + i, 8);             // 4 epilogue warps of each CTA
     }
+    mbar_init(a_ready, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns of both SMs of the pair
@@ -620,27 +622,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   cluster_sync_all();                          // the peer's barriers are initialised before anything is signalled there
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_acc = tmem_base;                  // columns [0, NBUF*128)
+  const uint32_t tmem_a = tmem_base + NBUF * TF2_BN;    // columns [NBUF*128, NBUF*128 + kpad/2)
 
   if (warp == 0) {
-    // ===== TMA producer (each CTA: its 128 queries' A block and its 128 rows of the B tile) =====
+    // ===== TMA producer: this CTA's 64 rows of every 128-row tile =====
     uint32_t stage = 0, phase = 0;
     for (uint32_t item = cluster_id; item < n_items; item += n_clusters) {
       const uint32_t chunk = item / n_pairs;
-      const uint32_t pair = item - chunk * n_pairs;
       const uint32_t t0 = chunk * a.tiles_per_chunk;
       const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-      const int q_row0 = (int)((pair * 2 + rank) * TF_BM);
       for (uint32_t t = t0; t < t1; ++t) {
-        const int x_row0 = (int)(t * TF2_BN + rank * TF_BM);
+        const int x_row0 = (int)(t * TF2_BN + rank * 64);
         for (uint32_t kb = 0; kb < KB; ++kb) {
-          mbar_wait_cluster(empty + stage, phase ^ 1);
+          mbar_wait(empty + stage, phase ^ 1);
           if (elect_one()) {
             const uint32_t full_leader = mapa_u32(smem_u32(full + stage), 0);
             if (rank == 0) mbar_expect_tx(full + stage, 2 * TF2_STAGE_BYTES);   // both CTAs' bytes
             else mbar_arrive_cluster(full_leader);
             unsigned char* st = sb + stage * TF2_STAGE_BYTES;
-            tma_load_2d_pair(st, &tmap_a, full_leader, (int)(kb * TF_BK), q_row0);
-            tma_load_2d_pair(st + TF_BM * TF_BK * 2, &tmap_b, full_leader, (int)(kb * TF_BK), x_row0);
+#pragma unroll
+            for (int h = 0; h < TF2_KSTEP / TF_BK; ++h)   // one 128-byte-wide box per 64 K elements
+              tma_load_2d_pair(st + h * (64 * TF_BK * 2), &tmap_b, full_leader, (int)(kb * TF2_KSTEP + h * TF_BK), x_row0);
           }
           __syncwarp();
           if (++stage == TF2_STAGES) {
@@ -653,30 +656,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   } else if (warp == 1) {
     if (rank == 0) {
       // ===== MMA issuer: one lane of the leader CTA drives the tensor cores of both SMs =====
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=256, M=256
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=256
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TF2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint64_t desc0 = make_b_desc(smem_u32(sb));
-      uint32_t stage = 0, phase = 0, acc_it = 0;
+      uint32_t stage = 0, phase = 0, acc_it = 0, a_phase = 0;
       for (uint32_t item = cluster_id; item < n_items; item += n_clusters) {
         const uint32_t chunk = item / n_pairs;
         const uint32_t t0 = chunk * a.tiles_per_chunk;
         const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
+        mbar_wait(a_ready, a_phase);   // both CTAs have their query blocks in TMEM
+        a_phase ^= 1;
+        tc_fence_after();
         for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
-          const uint32_t buf = acc_it & 1, use = acc_it >> 1;
-          mbar_wait_cluster(acc_empty + buf, (use & 1) ^ 1);
+          const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
+          const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
+          mbar_wait(acc_empty + buf, (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TF2_BN;
+          const uint32_t d_tmem = tmem_acc + buf * TF2_BN;
           for (uint32_t kb = 0; kb < KB; ++kb) {
-            mbar_wait_cluster(full + stage, phase);
+            mbar_wait(full + stage, phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t adesc = desc0 + (uint64_t)(stage * (TF2_STAGE_BYTES >> 4));
-              const uint64_t bdesc = adesc + (uint64_t)((TF_BM * TF_BK * 2) >> 4);
+              const uint64_t bdesc = desc0 + (uint64_t)(stage * (TF2_STAGE_BYTES >> 4));
+              const uint32_t a_col = tmem_a + kb * (TF2_KSTEP / 2);
 #pragma unroll
-              for (uint32_t k = 0; k < TF_BK / 16; ++k)   // 32 bytes further along the swizzled rows per K = 16
-                tc_mma_ss_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-              tc_commit_pair(empty + stage);                     // the slot is free in both CTAs once these MMAs retire
-              if (kb == KB - 1) tc_commit_pair(acc_full + buf);  // both epilogues may read their accumulators
+              for (uint32_t k = 0; k < TF2_KSTEP / 16; ++k) {
+                // A: 16 bf16 of K = 8 TMEM columns; B: 32 bytes further along the swizzled row, next 64-K box after four steps
+                const uint64_t boff = (uint64_t)((k >> 2) * ((64 * TF_BK * 2) >> 4) + (k & 3) * 2);
+                tc_mma_ts_pair(d_tmem, a_col + k * 8, bdesc + boff, idesc, (kb | k) != 0);
+              }
+              tc_commit_pair(empty + stage);                 // the slot is free in both CTAs once these MMAs retire
+              if (kb == KB - 1) tc_commit_pair(acc_full + buf);   // both epilogues may read their accumulators
             }
             __syncwarp();
             if (++stage == TF2_STAGES) {
@@ -697,7 +707,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     float* my_qs = s_qs + qrow;
     uint32_t* my_qc = s_qc + qrow;
     float* my_aux = s_aux + (warp - 2) * 2 * TF2_BN;
-    const uint32_t acc_empty_leader0 = mapa_u32(smem_u32(acc_empty), 0);
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
+    const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), 0);
     uint32_t acc_it = 0;
     const unsigned long long coef2 = pack_f32x2(a.coef, a.coef);
     for (uint32_t item = cluster_id; item < n_items; item += n_clusters) {
@@ -705,7 +716,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const uint32_t pair = item - chunk * n_pairs;
       const uint32_t t0 = chunk * a.tiles_per_chunk;
       const uint32_t t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-      const uint32_t q_global = (pair * 2 + rank) * TF_BM + qrow;
+      const uint32_t q_global = (pair * 2 + rank) * TF_BM + qrow;   // (< n_qblocks_pad * 128: the bf16 query array is padded to whole pairs)
+      // ---- A operand: this thread's query row -> its TMEM lane, packed bf16 pairs. All MMAs of the previous
+      // item have retired (its last acc_full was waited on), so A may be rewritten.
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)q_global * a.kpad);
+        const uint32_t n16 = a.kpad / 8;
+        for (uint32_t i = 0; i < n16; ++i) {
+          uint4 v = __ldg(src + i);
+          tc_st4(tmem_a + lane_addr + i * 4, v.x, v.y, v.z, v.w);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+      }
       float sc[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
@@ -720,102 +745,94 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
       float theta = hint;
       int imax = 0;
-      // additive term of the 256 columns of a tile: 8 floats per lane, fetched one tile ahead
-      auto load_aux = [&](uint32_t t, float4& lo, float4& hi) {
-        lo = hi = make_float4(INF, INF, INF, INF);
+      // additive term of the 128 columns of a tile: one float4 per lane, fetched one tile ahead
+      auto load_aux = [&](uint32_t t) -> float4 {
+        float4 r = make_float4(INF, INF, INF, INF);
         if (t < t1) {
-          const uint32_t c = t * TF2_BN + lane * 8;
-          if (c + 7 < a.n_rows) {
-            lo = __ldg(reinterpret_cast<const float4*>(a.aux + c));
-            hi = __ldg(reinterpret_cast<const float4*>(a.aux + c + 4));
+          const uint32_t c = t * TF2_BN + lane * 4;
+          if (c + 3 < a.n_rows) {
+            r = __ldg(reinterpret_cast<const float4*>(a.aux + c));
           } else {
-            float tmp[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) tmp[e] = (c + e < a.n_rows) ? __ldg(a.aux + c + e) : INF;
-            lo = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
-            hi = make_float4(tmp[4], tmp[5], tmp[6], tmp[7]);
+            if (c + 0 < a.n_rows) r.x = __ldg(a.aux + c + 0);
+            if (c + 1 < a.n_rows) r.y = __ldg(a.aux + c + 1);
+            if (c + 2 < a.n_rows) r.z = __ldg(a.aux + c + 2);
           }
         }
+        return r;
       };
-      float4 aux_lo, aux_hi;
-      load_aux(t0, aux_lo, aux_hi);
+      float4 aux_next = load_aux(t0);
       for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
-        const uint32_t buf = acc_it & 1, use = acc_it >> 1;
         float* aux_t = my_aux + (acc_it & 1) * TF2_BN;
-        reinterpret_cast<float4*>(aux_t)[lane * 2] = aux_lo;
-        reinterpret_cast<float4*>(aux_t)[lane * 2 + 1] = aux_hi;
-        load_aux(t + 1, aux_lo, aux_hi);
+        reinterpret_cast<float4*>(aux_t)[lane] = aux_next;
+        aux_next = load_aux(t + 1);
         __syncwarp();
-        mbar_wait_cluster(acc_full + buf, use & 1);
+        const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
+        const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
+        mbar_wait(acc_full + buf, use & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          float v[128];
+        float v[TF2_BN];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) tc_ld32(tmem_base + lane_addr + buf * TF2_BN + half * 128 + g * 32, v + g * 32);
-          tc_wait_ld();
-          if (half == 1) {
-            // both halves are in registers / done: hand the accumulator back to the MMA warp of the leader
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + buf * 8);
+        for (int g = 0; g < TF2_BN / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF2_BN + g * 32, v + g * 32);
+        tc_wait_ld();
+        // the accumulator now lives in registers: hand it back to the MMA warp of the leader before gating
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader + buf * 8);
+        const float4* aux4 = reinterpret_cast<const float4*>(aux_t);
+        const uint32_t colw = t * TF2_BN;
+#pragma unroll
+        for (int seg = 0; seg < TF2_BN / 16; ++seg) {
+          float4 ax[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ax[i] = aux4[seg * 4 + i];
+          float sg[16], mg[4];
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int j = seg * 16 + g4 * 4;
+            fma2(coef2, v[j + 0], v[j + 1], ax[g4].x, ax[g4].y, sg[g4 * 4 + 0], sg[g4 * 4 + 1]);
+            fma2(coef2, v[j + 2], v[j + 3], ax[g4].z, ax[g4].w, sg[g4 * 4 + 2], sg[g4 * 4 + 3]);
+            mg[g4] = fminf(min3(sg[g4 * 4 + 0], sg[g4 * 4 + 1], sg[g4 * 4 + 2]), sg[g4 * 4 + 3]);
           }
-          const float4* aux4 = reinterpret_cast<const float4*>(aux_t + half * 128);
-          const uint32_t colw = t * TF2_BN + half * 128;
-#pragma unroll
-          for (int seg = 0; seg < 8; ++seg) {
-            float4 ax[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ax[i] = aux4[seg * 4 + i];
-            float sg[16], mg[4];
+          if (fminf(min3(mg[0], mg[1], mg[2]), mg[3]) < theta) {
+            uint32_t cnt = 0;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               const int j = seg * 16 + g4 * 4;
-              fma2(coef2, v[j + 0], v[j + 1], ax[g4].x, ax[g4].y, sg[g4 * 4 + 0], sg[g4 * 4 + 1]);
-              fma2(coef2, v[j + 2], v[j + 3], ax[g4].z, ax[g4].w, sg[g4 * 4 + 2], sg[g4 * 4 + 3]);
-              mg[g4] = fminf(min3(sg[g4 * 4 + 0], sg[g4 * 4 + 1], sg[g4 * 4 + 2]), sg[g4 * 4 + 3]);
-            }
-            if (fminf(min3(mg[0], mg[1], mg[2]), mg[3]) < theta) {
-              uint32_t cnt = 0;
+              if (mg[g4] < theta) {
 #pragma unroll
-              for (int g4 = 0; g4 < 4; ++g4) {
-                const int j = seg * 16 + g4 * 4;
-                if (mg[g4] < theta) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (sg[g4 * 4 + e] < theta) {
-                      my_qs[cnt * ET] = sg[g4 * 4 + e];
-                      my_qc[cnt * ET] = colw + j + e;
-                      ++cnt;
-                    }
+                for (int e = 0; e < 4; ++e) {
+                  if (sg[g4 * 4 + e] < theta) {
+                    my_qs[cnt * ET] = sg[g4 * 4 + e];
+                    my_qc[cnt * ET] = colw + j + e;
+                    ++cnt;
                   }
                 }
               }
+            }
 #pragma unroll 1
-              for (uint32_t i = 0; i < cnt; ++i) {
-                const float s = my_qs[i * ET];
-                if (s < theta) {
-                  my_row[imax * ET] = my_qc[i * ET];
-                  float mv[KP];
-                  int mi[KP];
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const float s = my_qs[i * ET];
+              if (s < theta) {
+                my_row[imax * ET] = my_qc[i * ET];
+                float mv[KP];
+                int mi[KP];
 #pragma unroll
-                  for (int t2 = 0; t2 < KP; ++t2) {
-                    sc[t2] = (t2 == imax) ? s : sc[t2];
-                    mv[t2] = sc[t2];
-                    mi[t2] = t2;
-                  }
-#pragma unroll
-                  for (int w = KP / 2; w >= 1; w >>= 1) {
-#pragma unroll
-                    for (int t2 = 0; t2 < w; ++t2) {
-                      const bool gt = mv[t2 + w] > mv[t2];
-                      mv[t2] = gt ? mv[t2 + w] : mv[t2];
-                      mi[t2] = gt ? mi[t2 + w] : mi[t2];
-                    }
-                  }
-                  theta = fminf(mv[0], hint);
-                  imax = mi[0];
+                for (int t2 = 0; t2 < KP; ++t2) {
+                  sc[t2] = (t2 == imax) ? s : sc[t2];
+                  mv[t2] = sc[t2];
+                  mi[t2] = t2;
                 }
+#pragma unroll
+                for (int w = KP / 2; w >= 1; w >>= 1) {
+#pragma unroll
+                  for (int t2 = 0; t2 < w; ++t2) {
+                    const bool gt = mv[t2 + w] > mv[t2];
+                    mv[t2] = gt ? mv[t2 + w] : mv[t2];
+                    mi[t2] = gt ? mi[t2 + w] : mi[t2];
+                  }
+                }
+                theta = fminf(mv[0], hint);
+                imax = mi[0];
               }
             }
           }
@@ -845,11 +862,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 }
 
 template <int KP>
-static int32_t launch_filter2(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)TF2_STAGES * TF2_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 +
-                      (size_t)4 * 2 * TF2_BN * 4 + (size_t)(2 * TF2_STAGES + 4) * 8 + 16;
-  SCN_ALLOW_SMEM((tensor_filter2_kernel<KP>), smem);
-  tensor_filter2_kernel<KP><<<grid, 192, smem, stream>>>(tmap_b, tmap_a, fa);   // (cluster dims are compiled in)
+static size_t filter2_smem() {
+  return 1024 + (size_t)TF2_STAGES * TF2_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 + (size_t)4 * 2 * TF2_BN * 4 +
+         (size_t)(2 * TF2_STAGES + 5) * 8 + 16;
+}
+
+// CTA pairs that are resident at the same time (not every SM of the part has a free partner in its
+// TPC): the persistent grid is sized to it, so that no pair waits for a second wave.
+template <int KP>
+static int32_t filter2_resident_pairs(int* out) {
+  static int cached = 0;   // per process: one part per box
+  if (cached == 0) {
+    SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, 1>), filter2_smem<KP>());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 74);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = filter2_smem<KP>();
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tensor_filter2_kernel<KP, 1>, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 64;
+    }
+    cached = n;
+    if (getenv("SCN_DEBUG")) fprintf(stderr, "[scn] tensor_filter2<%d>: %d CTA pairs resident\n", KP, n);
+  }
+  *out = cached;
+  return SCN_OK;
+}
+
+template <int KP, int NBUF>
+static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, int pairs, cudaStream_t stream) {
+  SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, NBUF>), filter2_smem<KP>());
+  tensor_filter2_kernel<KP, NBUF><<<2 * pairs, 192, filter2_smem<KP>(), stream>>>(tmap_b, fa);   // (cluster dims are compiled in)
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -1134,24 +1178,26 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available from this driver");
   // CTA pairs (tensor_filter2_kernel) for long rows and batches of at least one full pair of query blocks
-  const bool pair_kernel = s->opt_tensor_pair != 0 && s->kpad >= (uint32_t)std::max<int64_t>(s->opt_tensor_pair_min_k, 128) && nq >= 256 &&
-                           !dbg_scores && (sms % 2) == 0;
+  const bool pair_kernel = s->opt_tensor_pair != 0 && (s->kpad == 512 || s->kpad == 640 || s->kpad == 768) && nq >= 256 && !dbg_scores &&
+                           (sms % 2) == 0;
   // 64-row tiles with two accumulators where one 128-column accumulator is all that fits next to A
   const bool half_tiles = !pair_kernel && (s->kpad == 640 || s->kpad == 768) && !dbg_scores && s->opt_tensor_bn != 128;
   const uint32_t BN = pair_kernel ? (uint32_t)TF2_BN : half_tiles ? 64u : 128u;
   const uint32_t n_rows = (uint32_t)s->rows;
   const uint32_t n_tiles = (n_rows + BN - 1) / BN;
   const uint32_t n_qb = (uint32_t)((nq + TF_BM - 1) / TF_BM);
-  const uint32_t nq_pad = n_qb * TF_BM;
-  uint32_t n_chunks = pair_kernel ? pick_chunks((n_qb + 1) / 2, n_tiles, (uint32_t)sms / 2) : pick_chunks(n_qb, n_tiles, (uint32_t)sms);
+  const uint32_t nq_pad = (pair_kernel ? (n_qb + 1) / 2 * 2 : n_qb) * TF_BM;   // whole pairs of query blocks
+  // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
+  uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
+  int resident_pairs = 0;
+  if (pair_kernel) SCN_TRY(kprime == 16 ? filter2_resident_pairs<16>(&resident_pairs) : filter2_resident_pairs<32>(&resident_pairs));
+  uint32_t n_chunks = pair_kernel ? pick_chunks((n_qb + 1) / 2, n_tiles, (uint32_t)resident_pairs) : pick_chunks(n_qb, n_tiles, (uint32_t)sms);
   if (s->opt_tensor_chunks > 0) n_chunks = (uint32_t)std::min<int64_t>(s->opt_tensor_chunks, n_tiles);
   uint32_t tiles_per_chunk = (n_tiles + n_chunks - 1) / n_chunks;
   n_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-  // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
-  uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
   // epilogue warps per TMEM lane quarter: the gate of a 128x128 tile costs ~1600 issue cycles with
   // one warp per quarter; the MMA of the tile takes 4*kpad cycles
-  const bool stream_a = s->kpad > TF_MAX_KPAD || pair_kernel;  // query block streamed with the rows (too wide for TMEM, or CTA pairs)
+  const bool stream_a = s->kpad > TF_MAX_KPAD;  // query block too wide for TMEM: stream it with the rows
   const uint32_t ew = (s->kpad >= 640 || dbg_scores || pair_kernel) ? 1u : 2u;
   const uint32_t n_lists = n_chunks * ew;  // candidate lists per query
   // few lists per query (huge batches) concentrate the global top-k in one list: at wide rows, where
@@ -1167,7 +1213,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   CUtensorMap tmap;
   cuuint64_t gdim[2] = {s->kpad, n_rows};
   cuuint64_t gstr[1] = {(cuuint64_t)s->kpad * 2};
-  cuuint32_t box[2] = {TF_BK, pair_kernel ? (cuuint32_t)TF_BM : BN};   // (a CTA of a pair loads 128 of the tile's 256 rows)
+  cuuint32_t box[2] = {TF_BK, pair_kernel ? 64u : BN};   // (a CTA of a pair loads 64 of the tile's 128 rows)
   cuuint32_t estr[2] = {1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, s->d_mirror, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1232,8 +1278,9 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   const bool two_buf = s->kpad <= 512;
   int32_t rc;
   if (pair_kernel) {
-    grid = 2 * (int)std::min<uint32_t>((uint32_t)sms / 2, ((n_qb + 1) / 2) * n_chunks);
-    rc = (kprime == 16) ? launch_filter2<16>(tmap, tmap_a, fa, grid, stream) : launch_filter2<32>(tmap, tmap_a, fa, grid, stream);
+    const int pairs = (int)std::min<uint32_t>((uint32_t)resident_pairs, ((n_qb + 1) / 2) * n_chunks);
+    if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2>(tmap, fa, pairs, stream) : launch_filter2<32, 2>(tmap, fa, pairs, stream);
+    else rc = (kprime == 16) ? launch_filter2<16, 1>(tmap, fa, pairs, stream) : launch_filter2<32, 1>(tmap, fa, pairs, stream);
   } else if (stream_a) {
     if (dbg_scores) rc = launch_filter<16, 2, 1, true, true, 128>(tmap, tmap_a, fa, grid, stream);
     else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream)

@@ -751,8 +751,6 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_bn = value;
   } else if (n == "tensor_pair") {
     s->opt_tensor_pair = value;
-  } else if (n == "tensor_pair_min_k") {
-    s->opt_tensor_pair_min_k = value;
   } else if (n == "tensor_chunks") {
     s->opt_tensor_chunks = value;
   } else if (n == "build_window") {

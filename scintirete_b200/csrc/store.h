@@ -80,8 +80,7 @@ struct scn_store {
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
-  int64_t opt_tensor_pair = 0;    // 1 = CTA-pair filter kernel (cta_group::2, M=256 x N=256 tiles) for long rows / large batches
-  int64_t opt_tensor_pair_min_k = 512;  // ... for kpad >= this
+  int64_t opt_tensor_pair = 1;    // 1 = CTA-pair filter kernel (cta_group::2, M=256 x N=128, queries stationary in TMEM) at kpad 512 / 640 / 768, batches >= 256
   int64_t opt_build_window = 0;   // scn_hnsw_insert: inserts searched speculatively per round; 0 = adaptive, 1 = none (serial)
   int64_t opt_profile = 0;
 

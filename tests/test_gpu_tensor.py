@@ -182,3 +182,31 @@ def test_small_batch_with_mass_ties_falls_back_to_the_full_sort_and_stays_exact(
     s.close()
     o = oracle.flat_search(1, db, q, k, nthreads=8)
     assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1])
+
+
+@pytest.mark.parametrize("metric", [DistanceMetric.L2, DistanceMetric.COSINE, DistanceMetric.INNER_PRODUCT])
+@pytest.mark.parametrize("n,d,nq,k", [(30001, 768, 300, 10), (20000, 600, 256, 24), (50000, 512, 1000, 10), (9000, 470, 513, 5)])
+def test_cta_pair_filter_equals_oracle(metric, n, d, nq, k):
+    # the tcgen05 cta_group::2 kernel (kpad 512 / 640 / 768, batches >= 256): an odd number of query blocks
+    # (the last pair is half empty), rows that do not fill the last 128-row tile, deleted rows, both k' sizes;
+    # ids and distance bits equal the oracle's and the single-CTA kernel's
+    db, q = gaussian(n, d, 31), gaussian(nq, d, 32)
+    db[n - 1] = db[3]
+    q[5] = db[3]
+    s = DeviceStore(d, metric)
+    s.append(db)
+    dead = np.array([4, n // 3, n - 5], np.uint64)
+    s.mark_deleted(dead)
+    deleted = np.zeros(n, np.uint8)
+    deleted[dead.astype(np.int64) - 1] = 1
+    s.set_option("flat_path", 2)
+    s.set_option("profile", 1)
+    s.set_option("tensor_pair", 1)
+    ids, dist, cnt = s.search_flat(q, k)
+    assert "tensor_filter" in s.last_timings()
+    s.set_option("tensor_pair", 0)
+    ids1, dist1, cnt1 = s.search_flat(q, k)
+    assert np.array_equal(ids, ids1) and np.array_equal(dist, dist1) and np.array_equal(cnt, cnt1)
+    o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, deleted=deleted, nthreads=8)
+    assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt)
+    s.close()
