@@ -329,7 +329,8 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "flat_path"         0 = auto, 1 = exact CUDA-core scan only, 2 = tensor-core filter + exact rerank
  *   "tensor_min_batch"  smallest batch that takes the tensor-core filter (default 1)
  *   "overfetch"         candidates kept per query and column block by the tensor filter (0 = auto)
- *   "tensor_hint"       1 = lists of a query start from the threshold of the finished ones (default)
+ *   "tensor_hint"       1 = lists of a query start from the threshold of the finished ones (default);
+ *                       "tensor_hint_target" rows of the shard that should beat a published threshold (0 = 3 k'')
  *   "tensor_bn"         128 forces 128-row tiles (0 = auto); "tensor_chunks" row chunks per query block (0 = auto)
  *   "tensor_pair"       1 = CTA-pair filter kernel (tcgen05 cta_group::2) for 448 < dim <= 512 and 576 < dim <= 768 at
  *                       batches of >= 256 queries (default), 0 = the single-CTA kernel everywhere

@@ -745,6 +745,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_hnsw_early = value;
   } else if (n == "hnsw_hash") {
     s->opt_hnsw_hash = value;
+  } else if (n == "tensor_hint_target") {
+    s->opt_tensor_hint_target = value;
   } else if (n == "tensor_hint") {
     s->opt_tensor_hint = value;
   } else if (n == "tensor_bn") {

@@ -78,6 +78,7 @@ struct scn_store {
   int64_t opt_hnsw_early = 1;     // hnsw_search: rows requested before the visited test (copies overlap the probes)
   int64_t opt_hnsw_hash = 0;      // hnsw_search: entries of the visited table of the first pass (shared or global memory); 0 = auto
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
+  int64_t opt_tensor_hint_target = 0;  // rows of the shard that should beat a published threshold; 0 = 3 k''
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
   int64_t opt_tensor_pair = 1;    // 1 = CTA-pair filter kernel (cta_group::2, M=256 x N=128, queries stationary in TMEM) at kpad 512 / 640 / 768, batches >= 256
