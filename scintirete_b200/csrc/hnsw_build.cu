@@ -87,6 +87,17 @@ struct BuildArgs {
   uint4* log;                // [n_slots][BUILD_LOGCAP] {row, W[ef-1] ord or LOG_NOT_FULL, admitted mask, layer | chunk << 8}
   uint32_t* log_cnt;         // [n_slots]
   unsigned long long* stats; // [0] distance evaluations, [1] expansions
+  // ---- search mode (ext_q != nullptr): the walk of HNSW.Search for external queries — the exact second pass
+  // of hnsw_search.cu for queries whose walk met a distance tie at the edge of W or overflowed its table
+  const float* ext_q;        // [.][dim]
+  const uint32_t* qlist;     // query indices
+  const uint32_t* nq_dev;    // device-resident number of listed queries
+  const uint64_t* ids;
+  uint32_t dim, k;
+  uint64_t* out_ids;
+  float* out_dist;
+  uint32_t* out_counts;
+  unsigned long long* failed;
 };
 
 __host__ __device__ inline size_t build_warp_bytes(uint32_t pitch, uint32_t ef_pad, uint32_t stage_bytes) {
@@ -277,14 +288,27 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
   uint32_t tag = 0;
   unsigned long long evals = 0, hops = 0;
 
-  for (uint32_t slot = blockIdx.x; slot < a.n_slots; slot += gridDim.x) {
-    const uint32_t x = a.q_rows[slot];
-    const int L = (int)a.q_levels[slot];
+  const bool search_mode = a.ext_q != nullptr;
+  const uint32_t n_slots = (search_mode && a.nq_dev) ? min(*a.nq_dev, a.n_slots) : a.n_slots;
+  for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    const uint32_t qi = search_mode ? (a.qlist ? a.qlist[slot] : slot) : slot;
+    const uint32_t x = search_mode ? 0u : a.q_rows[slot];
+    const int L = search_mode ? 0 : (int)a.q_levels[slot];
     __syncwarp();
-    for (uint32_t i = lane; i < a.pitch / 4; i += 32)
-      reinterpret_cast<float4*>(sq)[i] = __ldg(reinterpret_cast<const float4*>(a.vec + (size_t)x * a.pitch) + i);
-    const float qn = (METRIC == M_COS) ? __ldg(a.norm + x) : 0.0f;   // == the sequential norm of the query (store.cu prepare_rows)
-    uint4* log = a.log + (size_t)slot * BUILD_LOGCAP;
+    float qn = 0.0f;
+    if (search_mode) {
+      stage_query(sq, a.ext_q + (size_t)qi * a.dim, a.dim, a.pitch, lane, 32);
+      __syncwarp();
+      if (METRIC == M_COS) {
+        if (lane == 0) qn = exact_norm_padded(sq, a.pitch / 4);
+        qn = __shfl_sync(0xffffffffu, qn, 0);
+      }
+    } else {
+      for (uint32_t i = lane; i < a.pitch / 4; i += 32)
+        reinterpret_cast<float4*>(sq)[i] = __ldg(reinterpret_cast<const float4*>(a.vec + (size_t)x * a.pitch) + i);
+      if (METRIC == M_COS) qn = __ldg(a.norm + x);   // == the sequential norm of the query (store.cu prepare_rows)
+    }
+    uint4* log = a.log ? a.log + (size_t)slot * BUILD_LOGCAP : nullptr;
     uint32_t n_log = 0;
     bool overflow = false;
     uint32_t n_eps = 0;
@@ -380,14 +404,23 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
           const uint64_t key = ((uint64_t)od << 32) | ((uint64_t)(seq + rank) << 1);
           seq += __popc(mask);
           const uint32_t mask_in = merge_admitted(w, snk, snr, cand, key, nb, ef, cap, lane);
-          if (lane == 0 && n_log < BUILD_LOGCAP) log[n_log] = make_uint4(cur, worst, mask_in, (uint32_t)lc | ((c0 >> 5) << 8));
+          if (log && lane == 0 && n_log < BUILD_LOGCAP) log[n_log] = make_uint4(cur, worst, mask_in, (uint32_t)lc | ((c0 >> 5) << 8));
           ++n_log;
         }
       }
       if (overflow) break;
       // ---- result of this layer (hnsw.go:551-556), entry points of the next (hnsw.go:220, 248)
       __syncwarp();
-      if (lc <= L) {
+      if (search_mode) {
+        if (lc == 0) {   // hnsw.go:317-347: the first min(TopK, |W|) candidates (none is deleted, all are sorted)
+          const uint32_t n_out = min(a.k, w.cnt);
+          for (uint32_t i = lane; i < a.k; i += 32) {
+            a.out_ids[(size_t)qi * a.k + i] = (i < n_out) ? a.ids[w.row[i]] : 0ull;
+            a.out_dist[(size_t)qi * a.k + i] = (i < n_out) ? ord_f32((uint32_t)(w.key[i] >> 32)) : INF;
+          }
+          if (lane == 0 && a.out_counts) a.out_counts[qi] = n_out;
+        }
+      } else if (lc <= L) {
         const size_t o = ((size_t)a.out_off[slot] + lc) * a.efc;
         for (uint32_t i = lane; i < w.cnt; i += 32) {
           a.w_rows[o + i] = w.row[i];
@@ -399,7 +432,20 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
       for (uint32_t i = lane; i < n_eps; i += 32) eps[i] = w.row[i];
       __syncwarp();
     }
-    if (lane == 0) a.log_cnt[slot] = overflow ? LOG_OVERFLOW : n_log;
+    if (search_mode) {
+      if (overflow) {   // the largest table overflowed too: no result rather than a truncated beam
+        for (uint32_t i = lane; i < a.k; i += 32) {
+          a.out_ids[(size_t)qi * a.k + i] = 0ull;
+          a.out_dist[(size_t)qi * a.k + i] = INF;
+        }
+        if (lane == 0) {
+          if (a.out_counts) a.out_counts[qi] = 0;
+          atomicAdd(a.failed, 1ull);
+        }
+      }
+    } else if (lane == 0) {
+      a.log_cnt[slot] = overflow ? LOG_OVERFLOW : n_log;
+    }
   }
   if (a.stats && lane == 0) {
     atomicAdd(a.stats + 0, evals);
@@ -734,6 +780,60 @@ static int32_t build_search(int metric, const BuildArgs& a, uint32_t nb, int gri
     case M_COS: return build_search_metric<M_COS>(a, nb, grid, smem, st, launch, per_sm);
     default: return build_search_metric<M_IP>(a, nb, grid, smem, st, launch, per_sm);
   }
+}
+
+// The exact walk for the queries listed in d_qlist[0 .. *d_nq_dev): HNSW.Search with the reference's tie rules
+// (see WState). Always enqueued behind hnsw_search_kernel; exits at once when the list is empty.
+int32_t hnsw_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlist, const uint32_t* d_nq_dev, uint64_t nq, uint32_t k,
+                          uint32_t ef, uint32_t hash_size, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                          unsigned long long* d_failed, cudaStream_t st, Scratch& scratch) {
+  int sms = 0;
+  SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  const uint32_t ef_pad = std::max(64u, round_up(2 * ef, 32));
+  const uint32_t n_chunks = (s->pitch * 4 + 511) / 512;
+  const uint32_t nb = n_chunks <= 1 ? 1u : n_chunks <= 2 ? 2u : n_chunks <= 4 ? 4u : 6u;
+  const size_t smem = build_warp_bytes(s->pitch, ef_pad, ga_stage_bytes(512, nb));
+  if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "ef=%u / dim=%u need more shared memory than one SM has", ef, s->dim);
+  int per_sm = 0;
+  SCN_TRY(build_search(s->metric, BuildArgs{}, nb, 0, smem, st, false, &per_sm));
+  if (per_sm < 1) return fail(SCN_ERR_INVALID_PARAMETERS, "the exact walk kernel does not fit an SM");
+  // the tables live in global memory: bound their total (flagged queries are few)
+  const uint64_t max_blocks = std::max<uint64_t>(1, ((uint64_t)512 << 20) / ((uint64_t)hash_size * 4));
+  const int grid = (int)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms * per_sm, max_blocks), nq);
+  BuildArgs a{};
+  a.vec = s->d_vec;
+  a.norm = s->d_norm;
+  a.deleted = s->d_deleted;
+  a.adj0 = s->d_adj0;
+  a.adj_up = s->d_adj_up;
+  a.levels = s->d_levels;
+  a.up_off = s->d_up_off;
+  a.pitch = s->pitch;
+  a.n_rows = (uint32_t)s->rows;
+  a.s0 = 2 * (uint32_t)s->m;
+  a.su = (uint32_t)s->m;
+  a.has_deleted = (s->live != s->rows) ? 1u : 0u;
+  a.entry_row = s->entry_row;
+  a.max_layer = s->max_layer;
+  a.n_slots = (uint32_t)nq;
+  a.efc = ef;
+  a.ef_pad = ef_pad;
+  SCN_TRY(scratch.alloc(&a.ghash, (size_t)grid * hash_size));
+  a.hash_size = hash_size;
+  a.row_bits = 1;
+  while ((1ull << a.row_bits) <= (uint64_t)s->rows) ++a.row_bits;
+  a.tag_max = (uint32_t)((1ull << (32 - a.row_bits)) - 1);
+  a.ext_q = d_q;
+  a.qlist = d_qlist;
+  a.nq_dev = d_nq_dev;
+  a.ids = s->d_ids;
+  a.dim = s->dim;
+  a.k = k;
+  a.out_ids = d_out_ids;
+  a.out_dist = d_out_dist;
+  a.out_counts = d_out_counts;
+  a.failed = d_failed;
+  return build_search(s->metric, a, nb, grid, smem, st, true, nullptr);
 }
 
 }  // namespace scn

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
     uint32_t* orow = wrow1;
     uint32_t cnt = 0;
     bool overflow = false;
+    bool tie = false;   // an element left W with the very distance W[ef-1] now has: the reference may still expand it
     uint32_t cur = a.entry_row;
     const bool have_entry = (cur != ROW_NONE) && (cur < a.n_rows) && !bit_test(a.deleted, cur) && a.max_layer >= 0;
     if (have_entry) {
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
         const bool mine = (uint32_t)lane < nn;
         const uint64_t nkey = mine ? snk[lane] : KEY_NONE;
         uint32_t npos = 0;  // #{old < nkey} + #{new < nkey}
+        uint32_t dropped = 0xFFFFFFFFu;   // smallest ord(distance) among the entries that do not make the cut
         for (uint32_t i0 = 0; i0 < cnt; i0 += 128) {
           uint64_t kv[4];
           uint32_t rw[4], below[4];
@@ -401,6 +403,8 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
             if (i < cnt && pos < ef) {
               okey[pos] = kv[u];
               orow[pos] = rw[u];
+            } else if (i < cnt) {
+              dropped = min(dropped, (uint32_t)(kv[u] >> 32));
             }
           }
         }
@@ -408,11 +412,19 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
         if (mine && npos < ef) {
           okey[npos] = nkey;
           orow[npos] = snr[lane];
+        } else if (mine) {
+          dropped = min(dropped, (uint32_t)(nkey >> 32));
         }
         // a new (un-expanded) entry may have landed in front of p_lo
         p_lo = min(p_lo, __reduce_min_sync(0xffffffffu, mine ? npos : 0xFFFFFFFFu));
         cnt = min(ef, cnt + nn);
         __syncwarp();
+        // Exact-tie rules of the reference (candidates pushed out of W that still equal W[ef-1] stay expandable
+        // in `dynamic`, hnsw.go:516-518; neighbours of one list are admitted one by one, 536-542) differ from
+        // this merge only when a dropped entry ties with the new W[ef-1]: such a walk is redone by the exact
+        // walk kernel (hnsw_build.cu, WState) in the second pass. Never happens on data without equal distances.
+        dropped = __reduce_min_sync(0xffffffffu, dropped);
+        if (cnt == ef && dropped == (uint32_t)(okey[ef - 1] >> 32)) tie = true;
         uint64_t* tk = wkey;
         wkey = okey;
         okey = tk;
@@ -422,16 +434,12 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
       }
     }
 
-    if (overflow && a.overflow_list) {
+    if (overflow || tie) {
       if (lane == 0) {
         uint32_t slot = atomicAdd(a.overflow_count, 1u);
         a.overflow_list[slot] = qi;
       }
-      continue;  // the overflow pass will produce this query's results
-    }
-    if (overflow) {  // the overflow pass ran out of table as well: no result rather than a truncated beam
-      cnt = 0;
-      if (lane == 0) atomicAdd(a.failed, 1ull);
+      continue;  // the second pass (exact walk, large table) will produce this query's results
     }
 
     // ---- result: the first min(k, |W|) entries, already in (distance, admission) order --------
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
 }
 
 template <int METRIC, int GM>
-static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
+static int32_t launch_hnsw(scn_store* s_, HnswArgs& a, int sms, cudaStream_t stream, Scratch& scratch, Profiler* prof) {
   // pass 1: shared-memory visited table (or, global_first, a table of the same size in global memory)
   const int warps = GM ? 1 : HNSW_MAX_WARPS;
   const uint32_t stages = gm_bytes(GM);
@@ -489,26 +497,15 @@ static int32_t launch_hnsw(HnswArgs& a, int sms, cudaStream_t stream, Scratch& s
     SCN_LAUNCHED();
     if (prof) prof->end();
   }
-  // pass 2 (always enqueued, exits at once when nothing overflowed): global-memory visited table
-  HnswArgs b = a;
-  b.qlist = a.overflow_list;
-  b.nq_dev = a.overflow_count;
-  b.overflow_list = nullptr;
-  // 2x the row count — a table that cannot fill up — capped at 4 M entries (16 MB per resident query;
-  // a walk that visits more than 3.6 M rows is reported as failed, scn_search_hnsw returns 5001)
-  b.hash_size = (uint32_t)std::min<uint64_t>((uint64_t)1 << 22, next_pow2(a.n_rows) * 2ull);
-  b.hash_size = std::max<uint32_t>(b.hash_size, 1024u);
-  const size_t smem2 = hnsw_warp_bytes(a.pitch, a.ef_pad, 0, true, stages) * warps;
-  SCN_ALLOW_SMEM((hnsw_search_kernel<METRIC, true, GM>), smem2);
-  int per_sm2 = 0;
-  SCN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, hnsw_search_kernel<METRIC, true, GM>, warps * 32, smem2));
-  // the tables live in global memory (1-4 MB per warp at the largest size): bound their total
-  const uint64_t max_blocks2 = std::max<uint64_t>(1, ((uint64_t)512 << 20) / ((uint64_t)warps * b.hash_size * 4));
-  const int grid2 = (int)std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms * std::max(per_sm2, 1), max_blocks2), blocks_needed);
-  SCN_TRY(scratch.alloc(&b.ghash, (size_t)grid2 * warps * b.hash_size));
-  if (prof) prof->begin("hnsw_search_overflow");
-  hnsw_search_kernel<METRIC, true, GM><<<grid2, warps * 32, smem2, stream>>>(b);
-  SCN_LAUNCHED();
+  // pass 2 (always enqueued, exits at once when its list is empty): the exact walk kernel of hnsw_build.cu for
+  // the queries whose visited table overflowed or whose walk met a distance tie at the edge of W. Table: 2x
+  // the row count — one that cannot fill up — capped at 4 M entries (16 MB per resident query; a walk that
+  // visits more than 3.6 M rows is reported as failed, scn_search_hnsw returns 5001).
+  uint32_t hash2 = (uint32_t)std::min<uint64_t>((uint64_t)1 << 22, next_pow2(a.n_rows) * 2ull);
+  hash2 = std::max<uint32_t>(hash2, 1024u);
+  if (prof) prof->begin("hnsw_search_exact");
+  SCN_TRY(hnsw_search_exact(s_, a.q, a.overflow_list, a.overflow_count, a.nq, a.k, a.ef, hash2, a.out_ids, a.out_dist, a.out_counts, a.failed,
+                            stream, scratch));
   if (prof) prof->end();
   return SCN_OK;
 }
@@ -575,10 +572,10 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   int32_t rc;
 #define HN(MT)                                                                  \
   switch (gm) {                                                                 \
-    case 0: rc = launch_hnsw<MT, 0>(a, sms, stream, scratch, prof); break;      \
-    case 1: rc = launch_hnsw<MT, 1>(a, sms, stream, scratch, prof); break;      \
-    case 2: rc = launch_hnsw<MT, 2>(a, sms, stream, scratch, prof); break;      \
-    default: rc = launch_hnsw<MT, 3>(a, sms, stream, scratch, prof); break;     \
+    case 0: rc = launch_hnsw<MT, 0>(s, a, sms, stream, scratch, prof); break;      \
+    case 1: rc = launch_hnsw<MT, 1>(s, a, sms, stream, scratch, prof); break;      \
+    case 2: rc = launch_hnsw<MT, 2>(s, a, sms, stream, scratch, prof); break;      \
+    default: rc = launch_hnsw<MT, 3>(s, a, sms, stream, scratch, prof); break;     \
   }
   switch (s->metric) {
     case M_L2: HN(M_L2); break;

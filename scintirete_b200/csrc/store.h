@@ -206,6 +206,9 @@ int32_t tensor_debug_scores(scn_store* s, const float* d_q, uint64_t nq, float* 
 int32_t mark_aux_deleted(scn_store* s, const uint32_t* h_rows, uint32_t n, cudaStream_t stream);
 int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                     float* d_out_dist, uint32_t* d_out_counts, cudaStream_t stream, Profiler* prof);
+int32_t hnsw_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlist, const uint32_t* d_nq_dev, uint64_t nq, uint32_t k,
+                          uint32_t ef, uint32_t hash_size, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                          unsigned long long* d_failed, cudaStream_t st, Scratch& scratch);
 int32_t vector_ops(int32_t op, const float* d_a, const float* d_b, uint64_t n, uint32_t dim, float* d_out, cudaStream_t stream);
 int32_t distance_batch(int32_t metric, const float* d_q, uint64_t nq, const float* d_x, uint64_t nx, uint32_t dim,
                        float* d_out, cudaStream_t stream);

@@ -225,3 +225,22 @@ def test_restored_snapshot_keeps_a_deleted_entry_point_verbatim():
         g2.store.get([8])
     assert e.value.code == 3004
     assert np.array_equal(g2.store.get([9])[0], db[8])
+
+
+@pytest.mark.parametrize("n,d,hi,M,efc,metric,ef", [(3000, 8, 3, 8, 40, 1, 32), (3000, 16, 2, 16, 64, 1, 64), (4000, 12, 4, 16, 100, 2, 64),
+                                                    (3000, 24, 3, 16, 200, 3, 128), (500, 4, 1, 4, 16, 1, 8)])
+def test_search_follows_the_reference_through_exact_distance_ties(n, d, hi, M, efc, metric, ef):
+    # small integer coordinates: most distances tie exactly (last case: all vectors identical). The fast walk
+    # flags every query whose W dropped an entry that ties with W[ef-1]; those are redone by the exact walk
+    # (ghost candidates, sequential admission — hnsw.go:516-518, 536-542), so ids, distances and counts are
+    # the reference's even here
+    db = np.random.default_rng(5).integers(0, hi, (n, d)).astype(np.float32) + (0.0 if metric == 1 else 1.0)
+    q = np.random.default_rng(6).integers(0, hi, (300, d)).astype(np.float32) + (0.0 if metric == 1 else 1.0)
+    h = oracle.OracleHNSW(M=M, ef_construction=efc, ef_search=ef, max_layers=16, seed=42, metric=metric)
+    h.build(db)
+    g = GPUHNSWIndex(HNSWParams(m=M, ef_search=ef), DistanceMetric(metric), d)
+    g.import_graph_state(to_graph_state(h.export_graph_state(), M))
+    for k in (10, ef + 5):
+        ids, dist, cnt = g.search_batch(q, SearchParams(top_k=k, ef_search=ef))
+        o_ids, o_dist, o_cnt, _ = h.search_batch(q, k, ef, nthreads=4)
+        assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist)
