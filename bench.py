@@ -684,6 +684,27 @@ def bench_hnsw(ctx: Ctx, wl, name: str, ef: int, steps: int, warmup: int, cpu_ba
                           "recall_at_k_gpu": recall_at_k(h_ids.array[:nq], gt_ids), "recall_at_k_oracle_sample": recall_at_k(oi, gt_ids[:n_s]),
                           "identical_to_oracle_sample": bool(np.array_equal(h_ids.array[:n_s], oi))})
         cur_ef[0] = ef
+        # the same batch with exact tie handling on: walks that end on a distance tie at the edge of W are redone
+        store.set_option("hnsw_exact_ties", 1)
+        store.set_option("profile", 1)
+        for _ in range(2):
+            step_device()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step_device()
+        e1.record()
+        torch.cuda.synchronize()
+        redone = store.last_counters()[2]
+        step_e2e()
+        oi, _, _, _ = h.search_batch(hq.array[:n_s], k, ef, nthreads=threads)
+        exact_ties = {"value": nq * 5 / (e0.elapsed_time(e1) * 1e-3), "unit": "queries/s", "walks_redone_per_batch": int(redone),
+                      "identical_to_oracle_sample": bool(np.array_equal(h_ids.array[:n_s], oi)),
+                      "note": "option hnsw_exact_ties=1: results equal the reference's even through exact float ties; one re-walk is a "
+                              "single-warp latency chain"}
+        store.set_option("hnsw_exact_ties", 0)
+        store.set_option("profile", 0)
         block = {
             "workload": f"{name}: {rows}x{dim} {METRIC_NAME[metric]} hnsw k={k} nq={nq_total} ef={ef}",
             "value": nq_total / (ms_step * 1e-3), "unit": "queries/s", "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
@@ -700,7 +721,7 @@ def bench_hnsw(ctx: Ctx, wl, name: str, ef: int, steps: int, warmup: int, cpu_ba
                     "d2h_bytes_per_step": nq * (k * 12 + 4),
                     "timer": "host wall clock around the blocking host-buffer C-ABI call (scn_search_hnsw), pinned buffers"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "verified": verified,
-            "ef_sweep": sweep, "kernels_ms_per_step": {n_: v[0] / steps for n_, v in timings.items()}, "counters": counters,
+            "ef_sweep": sweep, "exact_ties": exact_ties, "kernels_ms_per_step": {n_: v[0] / steps for n_, v in timings.items()}, "counters": counters,
         }
     ctx.barrier()
     for b in (hq, h_ids, h_dist, h_cnt):

@@ -339,6 +339,11 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory
  *   "hnsw_hash"         entries of the visited table (0 = auto); "hnsw_per_sm" cap on resident queries per SM
  *   "hnsw_early"        1 = rows requested before the visited test (default)
+ *   "hnsw_exact_ties"   1 = a walk that ends while an element pushed out of the candidate list still has exactly the
+ *                       distance of its last entry (the reference would go on expanding it, hnsw.go:516-518) is redone
+ *                       by the exact walk kernel: results equal the reference's even through exact float ties. 0
+ *                       (default): such walks — 1 of 10 000 at 1M x 128 — are returned as they are (one re-walk is a
+ *                       single-warp latency chain, +0.9 ms on a 3.9 ms batch). The build (scn_hnsw_insert) is always exact.
  *   "build_window"      scn_hnsw_insert: inserts searched speculatively per round (0 = adaptive, 1 = none)
  *   "auto_id_base"      (empty store only) auto-assigned ids become value + row + 1: a row shard of a larger
  *                       collection numbers its rows globally
@@ -354,7 +359,8 @@ SCN_API int32_t scn_debug_tensor_scores(scn_store* s, const float* q, uint64_t n
 /* Counters of the last search. Flat: [0] queries served by the tensor path, [1] of those, queries
  * whose first certificate failed (all their chunk candidates were then reranked), [2] queries that
  * failed the second certificate too and were re-scanned exactly. HNSW (option "profile" = 1):
- * [0] distance evaluations, [1] expansions. */
+ * [0] distance evaluations, [1] expansions, [2] walks redone by the exact walk kernel (visited table
+ * overflow, or a distance tie at the edge of the candidate list that held to the end of the walk). */
 SCN_API int32_t scn_last_counters(scn_store* s, uint64_t* out, int32_t n);
 
 #ifdef __cplusplus

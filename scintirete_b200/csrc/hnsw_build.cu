@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
       __syncwarp();
     }
     if (search_mode) {
+      if (lane == 0 && a.stats) atomicAdd(a.stats + 2, 1ull);   // walks redone exactly
       if (overflow) {   // the largest table overflowed too: no result rather than a truncated beam
         for (uint32_t i = lane; i < a.k; i += 32) {
           a.out_ids[(size_t)qi * a.k + i] = 0ull;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(32) hnsw_build_search_kernel(BuildArgs a) {
       a.log_cnt[slot] = overflow ? LOG_OVERFLOW : n_log;
     }
   }
-  if (a.stats && lane == 0) {
+  if (a.stats && lane == 0 && !search_mode) {
     atomicAdd(a.stats + 0, evals);
     atomicAdd(a.stats + 1, hops);
   }
@@ -833,6 +834,7 @@ int32_t hnsw_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlis
   a.out_dist = d_out_dist;
   a.out_counts = d_out_counts;
   a.failed = d_failed;
+  a.stats = s->opt_profile ? s->d_counters : nullptr;
   return build_search(s->metric, a, nb, grid, smem, st, true, nullptr);
 }
 

@@ -68,6 +68,7 @@ struct HnswArgs {
   uint32_t has_deleted;    // 0: no row is soft-deleted, the bitmap need not be read
   uint32_t global_first;   // 1: the first pass keeps its visited tables in global memory too (L2-resident; more warps per SM)
   uint32_t early_issue;    // shared-memory gather: request the rows of a list before the visited test
+  uint32_t exact_ties;     // 1: a walk whose end state still holds a distance tie at the edge of W is redone exactly
   uint32_t entry_row;
   int32_t max_layer;
   const float* q;
@@ -147,7 +148,8 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
     uint32_t* orow = wrow1;
     uint32_t cnt = 0;
     bool overflow = false;
-    bool tie = false;   // an element left W with the very distance W[ef-1] now has: the reference may still expand it
+    bool tie = false;            // the reference's walk may go on where this one ends: redo it exactly (second pass)
+    uint32_t ghost_ord = 0xFFFFFFFFu;   // distance of an un-expanded element that left W with the very distance W[ef-1] had then
     uint32_t cur = a.entry_row;
     const bool have_entry = (cur != ROW_NONE) && (cur < a.n_rows) && !bit_test(a.deleted, cur) && a.max_layer >= 0;
     if (have_entry) {
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
               if (m) break;
             }
             if (!m) {
+              // every entry of W has been expanded; the reference would go on with a ghost that still ties with W[ef-1]
+              if (a.exact_ties && cnt >= ef && ghost_ord == reinterpret_cast<const uint32_t*>(wkey)[2 * (ef - 1) + 1]) tie = true;
               finished = true;
               break;
             }
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
             if (i < cnt && pos < ef) {
               okey[pos] = kv[u];
               orow[pos] = rw[u];
-            } else if (i < cnt) {
+            } else if (i < cnt && !(kv[u] & 1ull)) {   // (an expanded entry that leaves W is gone for good)
               dropped = min(dropped, (uint32_t)(kv[u] >> 32));
             }
           }
@@ -419,12 +423,14 @@ __global__ void __launch_bounds__(HNSW_MAX_WARPS * 32) hnsw_search_kernel(HnswAr
         p_lo = min(p_lo, __reduce_min_sync(0xffffffffu, mine ? npos : 0xFFFFFFFFu));
         cnt = min(ef, cnt + nn);
         __syncwarp();
-        // Exact-tie rules of the reference (candidates pushed out of W that still equal W[ef-1] stay expandable
-        // in `dynamic`, hnsw.go:516-518; neighbours of one list are admitted one by one, 536-542) differ from
-        // this merge only when a dropped entry ties with the new W[ef-1]: such a walk is redone by the exact
-        // walk kernel (hnsw_build.cu, WState) in the second pass. Never happens on data without equal distances.
+        // Exact-tie rule of the reference: an admitted, un-expanded element that is pushed out of W while its
+        // distance EQUALS the new W[ef-1] stays in `dynamic` and is still expanded if the tie holds when W has
+        // been worked off (hnsw.go:516-518 stops only at dist > W[ef-1].dist). Remember the tie; if it still
+        // holds at the end of the walk, the walk is redone by the exact walk kernel (hnsw_build.cu, WState) in
+        // the second pass. (A NEW key that misses the cut with that distance is treated alike: whether the
+        // reference's one-by-one admission, 536-542, had let it in is decided there.)
         dropped = __reduce_min_sync(0xffffffffu, dropped);
-        if (cnt == ef && dropped == (uint32_t)(okey[ef - 1] >> 32)) tie = true;
+        if (cnt == ef && dropped == (uint32_t)(okey[ef - 1] >> 32)) ghost_ord = dropped;
         uint64_t* tk = wkey;
         wkey = okey;
         okey = tk;
@@ -539,6 +545,7 @@ int32_t hnsw_search(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uin
   if (gm == 2 && a.pitch * 4 <= 512) gm = 1;  // a single stage needs no second buffer
   a.global_first = s->opt_hnsw_global ? 1u : 0u;
   a.early_issue = s->opt_hnsw_early ? 1u : 0u;
+  a.exact_ties = s->opt_hnsw_exact_ties ? 1u : 0u;
   a.max_per_sm = (uint32_t)std::max<int64_t>(0, s->opt_hnsw_per_sm);
   a.entry_row = s->entry_row;
   a.max_layer = s->max_layer;

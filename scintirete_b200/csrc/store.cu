@@ -743,6 +743,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_hnsw_per_sm = value;
   } else if (n == "hnsw_early") {
     s->opt_hnsw_early = value;
+  } else if (n == "hnsw_exact_ties") {
+    s->opt_hnsw_exact_ties = value;
   } else if (n == "hnsw_hash") {
     s->opt_hnsw_hash = value;
   } else if (n == "tensor_hint_target") {

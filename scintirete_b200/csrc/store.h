@@ -76,6 +76,7 @@ struct scn_store {
   int64_t opt_hnsw_global = 1;    // hnsw_search: 1 = visited tables of the first pass in global memory (L2) instead of shared memory
   int64_t opt_hnsw_per_sm = 0;    // hnsw_search, global tables: cap on resident queries per SM; 0 = whatever fits
   int64_t opt_hnsw_early = 1;     // hnsw_search: rows requested before the visited test (copies overlap the probes)
+  int64_t opt_hnsw_exact_ties = 0;  // hnsw_search: 1 = walks that end with a distance tie at the edge of W are redone by the exact walk kernel
   int64_t opt_hnsw_hash = 0;      // hnsw_search: entries of the visited table of the first pass (shared or global memory); 0 = auto
   int64_t opt_tensor_hint = 1;    // lists of a query seed their threshold from the finished ones
   int64_t opt_tensor_hint_target = 0;  // rows of the shard that should beat a published threshold; 0 = 3 k''

@@ -240,6 +240,7 @@ def test_search_follows_the_reference_through_exact_distance_ties(n, d, hi, M, e
     h.build(db)
     g = GPUHNSWIndex(HNSWParams(m=M, ef_search=ef), DistanceMetric(metric), d)
     g.import_graph_state(to_graph_state(h.export_graph_state(), M))
+    g.store.set_option("hnsw_exact_ties", 1)
     for k in (10, ef + 5):
         ids, dist, cnt = g.search_batch(q, SearchParams(top_k=k, ef_search=ef))
         o_ids, o_dist, o_cnt, _ = h.search_batch(q, k, ef, nthreads=4)
