@@ -334,6 +334,10 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "tensor_bn"         128 forces 128-row tiles (0 = auto); "tensor_chunks" row chunks per query block (0 = auto)
  *   "tensor_pair"       1 = CTA-pair filter kernel (tcgen05 cta_group::2) for 448 < dim <= 512 and 576 < dim <= 768 at
  *                       batches of >= 256 queries (default), 0 = the single-CTA kernel everywhere
+ *   "tensor_fused"      candidate merge, exact rerank and certificate behind the filter in one launch per batch
+ *                       (one block per query): 1 always, 0 never (three grids), -1 auto (batches of <= 2048 queries)
+ *   "pdl"               1 = the short kernels behind the tensor filter are launched chained (programmatic dependent
+ *                       launch: the start-up of a kernel overlaps the kernel before it), 0 = ordinary launches
  *   "hnsw_gather"       row gather of hnsw_search: -1 auto, 0 registers (LDG.256), 1 / 2 / 3 shared-memory
  *                       stages of 512 B / 2 x 512 B / 256 B; "hnsw_gather_long" the auto choice for rows > 512 B
  *   "hnsw_global"       1 = visited tables in global memory (default), 0 = in shared memory

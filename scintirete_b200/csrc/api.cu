@@ -49,7 +49,7 @@ int32_t scn_search_flat_dev(scn_store* s, const float* d_q, uint64_t nq, uint32_
   SCN_TRY(scratch.alloc(&d_keys, nq * k));
   SCN_TRY(flat_keys(s, d_q, nq, k, 0, d_keys, st, &prof));
   prof.begin("keys_to_results");
-  SCN_TRY(keys_to_results(s, d_keys, nq, 0, d_out_ids, d_out_dist, d_out_counts, k, st));
+  SCN_TRY(keys_to_results(s, d_keys, nq, 0, d_out_ids, d_out_dist, d_out_counts, k, st, s->rows > 0));   // (an empty store ends in a memset, not a kernel)
   prof.end();
   prof.collect();
   return SCN_OK;

@@ -40,8 +40,46 @@ int static_smem_of(const void* kernel);
     if ((size_t)(bytes) > (size_t)limit__)                                                                \
       return scn::fail(SCN_ERR_INVALID_PARAMETERS, "%zu bytes of shared memory exceed the device limit",   \
                        (size_t)(bytes));                                                                  \
-    SCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit__));         \
+    /* once per kernel and device: the value never changes, so racing first calls are harmless */         \
+    static std::atomic<uint64_t> done__{0};                                                               \
+    int dev__ = 0;                                                                                        \
+    cudaGetDevice(&dev__);                                                                                \
+    const uint64_t bit__ = 1ull << (dev__ & 63);                                                          \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                                              \
+      SCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit__));       \
+      done__.fetch_or(bit__, std::memory_order_release);                                                  \
+    }                                                                                                     \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The kernels behind the filter of a small batch run for a few microseconds each, less than the gap
+// between two dependent launches. A kernel launched with launch_chained(..., pdl = true) may become
+// resident as soon as every block of the kernel before it has executed pdl_trigger() (or exited); it
+// must execute pdl_wait() before it touches anything an earlier kernel of the stream wrote — the wait
+// returns when the preceding grid has completed and its writes are visible. Every thread of such a
+// kernel waits at its top (a grid whose threads all left without waiting would complete early and
+// release ITS dependents before the grids further up the chain are done). Both instructions are
+// no-ops in a kernel that was launched the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // after a kernel launch
 #define SCN_LAUNCHED()                                                         \

@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
   __shared__ float s_qnorm[QB];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
   uint32_t nq_total = p.nq_dev ? min(*p.nq_dev, p.nq) : p.nq;
   const uint32_t n_tiles = (p.n_rows + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t n_chunks = p.dim_pad / SCAN_KC;
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const uint64_t* __r
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw);  // [cap]
   uint32_t q = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (nq_dev && q >= *nq_dev) return;
   for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) buf[i] = KEY_NONE;
   const uint64_t total = (uint64_t)n_parts * k;
@@ -245,20 +249,20 @@ static size_t scan_smem_bytes(int qb, uint32_t dim_pad, uint32_t k) {
 }
 
 template <int METRIC, int QB>
-static int32_t launch_scan(const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+static int32_t launch_scan(const ScanParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   SCN_ALLOW_SMEM((flat_exact_scan_kernel<METRIC, QB>), smem);
-  flat_exact_scan_kernel<METRIC, QB><<<grid, SCAN_THREADS, smem, stream>>>(p);
+  SCN_CUDA(launch_chained(flat_exact_scan_kernel<METRIC, QB>, dim3(grid), dim3(SCAN_THREADS), smem, stream, pdl, p));
   SCN_LAUNCHED();
   return SCN_OK;
 }
 
 template <int METRIC>
-static int32_t launch_scan_qb(int qb, const ScanParams& p, int grid, size_t smem, cudaStream_t stream) {
+static int32_t launch_scan_qb(int qb, const ScanParams& p, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   switch (qb) {
-    case 1: return launch_scan<METRIC, 1>(p, grid, smem, stream);
-    case 2: return launch_scan<METRIC, 2>(p, grid, smem, stream);
-    case 4: return launch_scan<METRIC, 4>(p, grid, smem, stream);
-    default: return launch_scan<METRIC, 8>(p, grid, smem, stream);
+    case 1: return launch_scan<METRIC, 1>(p, grid, smem, stream, pdl);
+    case 2: return launch_scan<METRIC, 2>(p, grid, smem, stream, pdl);
+    case 4: return launch_scan<METRIC, 4>(p, grid, smem, stream, pdl);
+    default: return launch_scan<METRIC, 8>(p, grid, smem, stream, pdl);
   }
 }
 
@@ -301,20 +305,23 @@ int32_t flat_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlis
   p.k = k;
   p.row_base = (uint32_t)row_base;
   p.partial = d_partial;
+  // behind the tensor path this is the last resort and normally has nothing to do: chained launches (see
+  // common.cuh) let its start-up overlap the kernels before it
+  const bool pdl = s->opt_pdl != 0 && d_nq_dev != nullptr && !(prof && prof->on);
   if (prof) prof->begin("flat_exact_scan");
   int32_t rc;
   switch (s->metric) {
-    case M_L2: rc = launch_scan_qb<M_L2>(qb, p, grid, smem, stream); break;
-    case M_COS: rc = launch_scan_qb<M_COS>(qb, p, grid, smem, stream); break;
-    default: rc = launch_scan_qb<M_IP>(qb, p, grid, smem, stream); break;
+    case M_L2: rc = launch_scan_qb<M_L2>(qb, p, grid, smem, stream, pdl); break;
+    case M_COS: rc = launch_scan_qb<M_COS>(qb, p, grid, smem, stream, pdl); break;
+    default: rc = launch_scan_qb<M_IP>(qb, p, grid, smem, stream, pdl); break;
   }
   if (prof) prof->end();
   SCN_TRY(rc);
   const uint32_t kp = std::max(32u, next_pow2(k));
   if (prof) prof->begin("merge_partials");
   const uint32_t cap = std::max(2 * kp, 2048u);
-  merge_partials_kernel<<<(unsigned)nq, 256, cap * sizeof(uint64_t), stream>>>(d_partial, (uint32_t)grid, (uint32_t)nq,
-                                                                              d_qlist, d_nq_dev, k, kp, cap, d_out_keys);
+  SCN_CUDA(launch_chained(merge_partials_kernel, dim3((unsigned)nq), dim3(256), cap * sizeof(uint64_t), stream, pdl, d_partial, (uint32_t)grid,
+                          (uint32_t)nq, d_qlist, d_nq_dev, k, kp, cap, d_out_keys));
   SCN_LAUNCHED();
   if (prof) prof->end();
   return SCN_OK;
@@ -325,6 +332,8 @@ __global__ void keys_to_results_kernel(const uint64_t* __restrict__ keys, uint64
                                        const uint64_t* __restrict__ ids, uint64_t* __restrict__ out_ids,
                                        float* __restrict__ out_dist, uint32_t* __restrict__ out_counts) {
   uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (q >= n) return;
   uint32_t cnt = 0;
   for (uint32_t j = 0; j < k; ++j) {
@@ -341,11 +350,12 @@ __global__ void keys_to_results_kernel(const uint64_t* __restrict__ keys, uint64
   if (out_counts) out_counts[q] = cnt;
 }
 
+// chained: the launch directly follows the kernels of flat_keys on the same stream (see launch_chained, common.cuh)
 int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64_t row_base, uint64_t* d_out_ids,
-                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream) {
+                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream, bool chained) {
   if (n == 0) return SCN_OK;
-  keys_to_results_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_keys, n, k, (uint32_t)row_base, s->d_ids,
-                                                                         d_out_ids, d_out_dist, d_out_counts);
+  SCN_CUDA(launch_chained(keys_to_results_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, stream, chained && s->opt_pdl != 0 && s->opt_profile == 0, d_keys,
+                          n, k, (uint32_t)row_base, s->d_ids, d_out_ids, d_out_dist, d_out_counts));
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -374,6 +384,8 @@ __global__ void __launch_bounds__(32) rerank_kernel(const float* __restrict__ ve
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_q + pitch);                       // [ncand_pad]
   unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_keys + ncand_pad);     // [2][32][528]
   const uint32_t lane = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t n_slots = nq_dev ? min(*nq_dev, nq) : nq;
   for (uint32_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
     const uint32_t qi = qlist ? qlist[slot] : slot;
@@ -429,12 +441,13 @@ int32_t rerank_rows(scn_store* s, const float* d_q, uint64_t nq, const uint32_t*
   size_t smem = rerank_smem_bytes(s->pitch, ncand_pad);
   if (smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many rerank candidates (%u)", ncand);
   const unsigned grid = d_qlist ? (unsigned)std::min<uint64_t>(nq, 148 * 6) : (unsigned)nq;
+  const bool pdl = s->opt_pdl != 0 && s->opt_profile == 0 && d_nq_dev != nullptr;   // the second-chance rerank of the tensor path
 #define RR(MT)                                                                                                    \
   do {                                                                                                            \
     SCN_ALLOW_SMEM((rerank_kernel<MT>), smem);                                                                    \
-    rerank_kernel<MT><<<grid, 32, smem, stream>>>(s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim,           \
-                                                  (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k,       \
-                                                  (uint32_t)row_base, d_qlist, d_nq_dev, (uint32_t)nq, d_out_keys); \
+    SCN_CUDA(launch_chained(rerank_kernel<MT>, dim3(grid), dim3(32), smem, stream, pdl, s->d_vec, s->d_norm, s->d_deleted, s->pitch, s->dim, \
+                            (uint32_t)s->rows, d_q, d_cand_rows, ncand, ncand_pad, k, (uint32_t)row_base, d_qlist, d_nq_dev, (uint32_t)nq,   \
+                            d_out_keys));                                                                                                 \
   } while (0)
   switch (s->metric) {
     case M_L2: RR(M_L2); break;

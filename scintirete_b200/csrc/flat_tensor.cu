@@ -249,9 +249,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   const uint32_t tmem_a = tmem_base + NBUF * TF_BN;       // columns [NBUF*BN, NBUF*BN + kpad/2)
 
   const uint32_t n_items = a.n_qblocks * a.n_chunks;
+  pdl_trigger();   // the kernels behind the filter may become resident as SMs free up (they wait for this grid to complete)
 
   if (warp == 0) {
     // ===== TMA producer (warp-uniform control flow; one elected lane issues) =====
+    // (the mirror is not written by the kernel before this one: the row tiles start to arrive at once)
+    if (ASM) pdl_wait();   // streamed queries: the A tiles are the bf16 rows prep_queries writes
     uint32_t stage = 0, phase = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint32_t chunk = item / a.n_qblocks;
@@ -333,6 +336,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
     constexpr int CW = TF_BN / EW;                     // columns per warp
     const uint32_t lane_addr = (quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
+    pdl_wait();   // bf16 queries and hints come from prep_queries (chained launch, common.cuh)
     uint32_t* my_row = s_crow + slice * 128 + qrow;    // slot j at [j*ET]
     float* my_qs = s_qs + slice * 128 + qrow;
     uint32_t* my_qc = s_qc + slice * 128 + qrow;
@@ -656,6 +660,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const uint32_t tmem_base = *s_tmem;
   const uint32_t tmem_acc = tmem_base;                  // columns [0, NBUF*128)
   const uint32_t tmem_a = tmem_base + NBUF * TF2_BN;    // columns [NBUF*128, NBUF*128 + kpad/2)
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer: this CTA's 64 rows of every 128-row tile =====
@@ -735,6 +740,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     const uint32_t qrow = quarter * 32 + lane;
     const uint32_t lane_addr = (quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
+    pdl_wait();   // bf16 queries and hints come from prep_queries (chained launch, common.cuh)
     uint32_t* my_row = s_crow + qrow;          // slot j at [j*ET]
     float* my_qs = s_qs + qrow;
     uint32_t* my_qc = s_qc + qrow;
@@ -931,9 +937,9 @@ static int32_t filter2_resident_pairs(int* out) {
 }
 
 template <int KP, int NBUF>
-static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, int pairs, cudaStream_t stream) {
+static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, int pairs, cudaStream_t stream, bool pdl) {
   SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, NBUF>), filter2_smem<KP>());
-  tensor_filter2_kernel<KP, NBUF><<<2 * pairs, 192, filter2_smem<KP>(), stream>>>(tmap_b, fa);   // (cluster dims are compiled in)
+  SCN_CUDA(launch_chained(tensor_filter2_kernel<KP, NBUF>, dim3(2 * pairs), dim3(192), filter2_smem<KP>(), stream, pdl, tmap_b, fa));   // (cluster dims are compiled in)
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -941,11 +947,19 @@ static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, i
 // ---- query preparation ---------------------------------------------------------------------------
 // One warp per query: bf16 row (zero padded to kpad), and the norms the certificate needs.
 // qstat[q] = {||q||, ||q~||, ||q - q~||, ||q~||^2}
+// The per-call initialisations ride along (they were three memsets): the published thresholds `hint`, the
+// two failure counts, and — first batch of a call — the device counters.
 __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
                                                            uint32_t kpad, __nv_bfloat16* __restrict__ qb,
-                                                           float4* __restrict__ qstat) {
+                                                           float4* __restrict__ qstat, uint32_t* __restrict__ hint,
+                                                           uint32_t* __restrict__ nfail, unsigned long long* __restrict__ counters) {
   uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();   // the filter may set itself up (barriers, TMEM, first row tiles) while the queries are converted
+  if (blockIdx.x == 0 && threadIdx.x < 4) {
+    if (threadIdx.x < 2) nfail[threadIdx.x] = 0;
+    if (counters) counters[threadIdx.x] = 0;
+  }
   if (qi >= nq_pad) return;
   float nn = 0.f, mm = 0.f, ee = 0.f;
   for (uint32_t i = lane; i < kpad; i += 32) {
@@ -962,33 +976,50 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
     mm += __shfl_xor_sync(0xffffffffu, mm, o);
     ee += __shfl_xor_sync(0xffffffffu, ee, o);
   }
-  if (lane == 0 && qi < nq) qstat[qi] = make_float4(sqrtf(nn), sqrtf(mm), sqrtf(ee), mm);
+  if (lane == 0 && qi < nq) {
+    qstat[qi] = make_float4(sqrtf(nn), sqrtf(mm), sqrtf(ee), mm);
+    hint[qi] = 0xFFFFFFFFu;
+  }
 }
 
 // ---- candidate merge: chunk lists -> k'' rows + tau -------------------------------------------------
-__global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __restrict__ cand_score,
-                                                               const uint32_t* __restrict__ cand_row,
-                                                               const float* __restrict__ chunk_tau, uint32_t n_chunks,
-                                                               uint32_t kprime, uint32_t n_pad, uint32_t kpp,
-                                                               uint32_t* __restrict__ out_rows, float* __restrict__ out_tau,
-                                                               float* __restrict__ out_tau_chunks) {
-  extern __shared__ __align__(16) unsigned char smem_merge[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_merge);  // [n_pad]
-  const uint32_t q = blockIdx.x;
-  const uint32_t n = n_chunks * kprime;
-  for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    uint64_t key = KEY_NONE;
-    if (i < n) {
-      uint32_t row = cand_row[(size_t)q * n + i];
-      if (row != ROW_NONE) key = make_key(cand_score[(size_t)q * n + i], row);
+// Bitonic sort of 64 keys by one warp: two keys per lane (elements lane and lane + 32), exchanges through
+// shuffles — no block barrier per step.
+__device__ __forceinline__ void warp_sort64(uint64_t* a, uint32_t lane) {
+  uint64_t x0 = a[lane], x1 = a[lane + 32];
+#pragma unroll
+  for (uint32_t size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {  // the partner is this lane's other element; size == 64: ascending
+        const uint64_t lo = x0 < x1 ? x0 : x1, hi = x0 < x1 ? x1 : x0;
+        x0 = lo;
+        x1 = hi;
+      } else {
+        const uint64_t y0 = __shfl_xor_sync(0xffffffffu, x0, stride), y1 = __shfl_xor_sync(0xffffffffu, x1, stride);
+        const bool lower = (lane & stride) == 0;                 // this element is the lower index of its pair
+        const bool up0 = (lane & size) == 0, up1 = ((lane + 32) & size) == 0;
+        const uint64_t mn0 = x0 < y0 ? x0 : y0, mx0 = x0 < y0 ? y0 : x0;
+        const uint64_t mn1 = x1 < y1 ? x1 : y1, mx1 = x1 < y1 ? y1 : x1;
+        x0 = (lower == up0) ? mn0 : mx0;
+        x1 = (lower == up1) ? mn1 : mx1;
+      }
     }
-    keys[i] = key;
   }
-  // Long lists (small batches spread a query block over ~148 row chunks: thousands of candidates,
-  // of which k'' + 1 matter): radix-select the score of rank k'' (4 passes over the 32 score bits),
-  // move the keys up to that score into a 256-entry buffer and sort only those. Many keys tied at
-  // the boundary (more than the buffer holds) fall through to the full sort below.
-  uint32_t n_sort = n_pad;
+  a[lane] = x0;
+  a[lane + 32] = x1;
+}
+
+// keys[0..max(n_pad, 64)) hold the n candidate keys of a query, KEY_NONE padded (the array has room for at least
+// 256 keys). On return keys[0..n_sort) are in ascending order and contain the kpp + 1 smallest keys (or all of
+// them); returns n_sort. Block-wide: every thread of the block calls it.
+// Long lists (small batches spread a query block over ~148 row chunks: thousands of candidates, of which
+// k'' + 1 matter): radix-select the score of rank k'' (4 passes over the 32 score bits), move the keys up to
+// that score into a 256-entry buffer and sort only those — by one warp when at most 64 are left, which is the
+// normal case (k'' + 1 = 33 unless scores tie). Many keys tied at the boundary (more than the buffer holds)
+// fall through to the full sort.
+__device__ __forceinline__ uint32_t select_and_sort(uint64_t* keys, uint32_t n, uint32_t n_pad, uint32_t kpp) {
+  uint32_t n_sort = n_pad < 64 ? 64u : n_pad;
   if (n_pad > 512) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank, s_cnt, s_total;
@@ -1053,28 +1084,57 @@ __global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __re
       }
     }
     __syncthreads();
-    if (s_cnt <= 256) {
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) keys[i] = buf[i];
-      n_sort = 256;
+    const uint32_t cnt = s_cnt;
+    if (cnt <= 256) {
+      n_sort = cnt <= 64 ? 64u : 256u;
+      for (uint32_t i = threadIdx.x; i < n_sort; i += blockDim.x) keys[i] = buf[i];
     }
   }
-  // block bitonic sort (ascending)
-  for (uint32_t size = 2; size <= n_sort; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (uint32_t t = threadIdx.x; t < n_sort / 2; t += blockDim.x) {
-        uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-        bool up = ((lo & size) == 0);
-        uint64_t x = keys[lo], y = keys[hi];
-        if ((x > y) == up) {
-          keys[lo] = y;
-          keys[hi] = x;
+  __syncthreads();
+  if (n_sort == 64) {
+    if (threadIdx.x < 32) warp_sort64(keys, threadIdx.x);
+  } else {
+    // block bitonic sort (ascending)
+    for (uint32_t size = 2; size <= n_sort; size <<= 1) {
+      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t t = threadIdx.x; t < n_sort / 2; t += blockDim.x) {
+          uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+          bool up = ((lo & size) == 0);
+          uint64_t x = keys[lo], y = keys[hi];
+          if ((x > y) == up) {
+            keys[lo] = y;
+            keys[hi] = x;
+          }
         }
+        __syncthreads();
       }
     }
   }
   __syncthreads();
+  return n_sort;
+}
+
+// (key of a candidate, KEY_NONE for an empty slot)
+__device__ __forceinline__ uint64_t candidate_key(const float* __restrict__ cand_score, const uint32_t* __restrict__ cand_row, size_t i) {
+  const uint32_t row = cand_row[i];
+  return row != ROW_NONE ? make_key(cand_score[i], row) : KEY_NONE;
+}
+
+__global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __restrict__ cand_score,
+                                                               const uint32_t* __restrict__ cand_row,
+                                                               const float* __restrict__ chunk_tau, uint32_t n_chunks,
+                                                               uint32_t kprime, uint32_t n_pad, uint32_t kpp,
+                                                               uint32_t* __restrict__ out_rows, float* __restrict__ out_tau,
+                                                               float* __restrict__ out_tau_chunks) {
+  extern __shared__ __align__(16) unsigned char smem_merge[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_merge);  // [max(n_pad, 256)]
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = n_chunks * kprime;
+  pdl_trigger();
+  pdl_wait();
+  for (uint32_t i = threadIdx.x; i < max(n_pad, 64u); i += blockDim.x) keys[i] = (i < n) ? candidate_key(cand_score, cand_row, (size_t)q * n + i) : KEY_NONE;
+  __syncthreads();
+  const uint32_t n_sort = select_and_sort(keys, n, n_pad, kpp);
   for (uint32_t i = threadIdx.x; i < kpp; i += blockDim.x) {
     uint64_t key = (i < n_sort) ? keys[i] : KEY_NONE;
     out_rows[(size_t)q * kpp + i] = (key == KEY_NONE) ? ROW_NONE : (uint32_t)key;
@@ -1100,56 +1160,55 @@ __global__ void __launch_bounds__(512) merge_candidates_kernel(const float* __re
 // the reference distance of such a row is bounded below by LB (per metric, see below). The query is
 // certified iff LB > d_k strictly, so neither a closer row nor a tie with a lower row index can have
 // been missed. Anything else goes to the exact scan.
+__device__ __forceinline__ bool certificate_holds(uint64_t kth_key, float t, const float4 st, const float* __restrict__ bounds,
+                                                  uint32_t dim, uint32_t kpad, int metric) {
+  const float INF = __int_as_float(0x7f800000);
+  const float dk = (kth_key == KEY_NONE) ? INF : ord_f32((uint32_t)(kth_key >> 32));
+  if (t == INF) return true;      // nothing was left out: the rerank saw every live row
+  if (!(dk < INF)) return false;  // fewer than k finite results although rows were left out
+  const float qn = st.x, qtn = st.y, eq = st.z, qtn2 = st.w;
+  const float Mmax = bounds[0], Emax = bounds[1], Xmax = bounds[2];
+  const float u = 5.9604645e-8f;  // 2^-24
+  const float etc = 8.0f * (float)kpad * u * qtn * Mmax;
+  const float E = (eq * Mmax + qn * Emax + etc) * 1.0001f;
+  const float g = 1.01f * (float)(dim + 2) * u;
+  float lb;
+  if (metric == M_IP) {
+    // d_ref(x) = -fl(q.x) >= -(q.x) - g*||q||*||x|| ;  -(q.x) >= s~ - E >= tau - E
+    lb = t - E - g * qn * Xmax;
+    lb -= fabsf(lb) * 4.0f * u;
+  } else if (metric == M_COS) {
+    // mirror rows are x/||x|| (fp32 divide, rel. error <= 2^-23 per element): -(q.x^) >= tau - E - ||q||*2^-22
+    // cos(x) = (q.x^)/||q|| <= (E' - tau)/||q||;  d_ref >= 1 - cos - (2g + 2^-21)
+    float Ep = E + qn * 4.0f * u;
+    float c = (Ep - t) / qn;
+    lb = 1.0f - c - (2.0f * g + 8.0f * u);
+    lb -= fabsf(lb) * 4.0f * u + 4.0f * u;
+    if (!(qn > 0.0f)) lb = -INF;  // zero query: every distance is exactly 1 -> ties everywhere
+  } else {
+    // ||q - x|| >= ||q~ - x~|| - ||q - q~|| - ||x - x~||, and ||q~ - x~||^2 = ||q~||^2 + s~ (s~ = ||x~||^2 - 2 q~.x~)
+    // fp32 error of s~: 2*e_tc plus the rounding of aux and of ||q~||^2 (<= K*2^-23 relative each)
+    float es = 2.0f * etc + (float)kpad * 2.0f * u * (Mmax * Mmax + qtn2);
+    float r2 = qtn2 + t - es;
+    float r = r2 > 0.0f ? sqrtf(r2) * (1.0f - 2.0f * u) : 0.0f;
+    lb = r - eq * 1.0001f - Emax;
+    lb = lb * (1.0f - g) * (1.0f - 4.0f * u);
+  }
+  return lb > dk;
+}
+
 __global__ void certify_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ tau, const float4* __restrict__ qstat,
                                const float* __restrict__ bounds, uint32_t nq, uint32_t k, uint32_t dim, uint32_t kpad,
                                int metric, const uint32_t* __restrict__ qlist_in, const uint32_t* __restrict__ nq_in_dev,
                                uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count,
                                unsigned long long* __restrict__ counters, int counter_slot) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t n_slots = nq_in_dev ? min(*nq_in_dev, nq) : nq;
   uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
   const uint32_t q = qlist_in ? qlist_in[slot] : slot;
-  const float INF = __int_as_float(0x7f800000);
-  uint64_t kk = keys[(size_t)q * k + (k - 1)];
-  float dk = (kk == KEY_NONE) ? INF : ord_f32((uint32_t)(kk >> 32));
-  float t = tau[q];
-  bool ok;
-  if (t == INF) {
-    ok = true;  // nothing was left out: the rerank saw every live row
-  } else if (!(dk < INF)) {
-    ok = false;  // fewer than k finite results although rows were left out
-  } else {
-    float4 st = qstat[q];
-    const float qn = st.x, qtn = st.y, eq = st.z, qtn2 = st.w;
-    const float Mmax = bounds[0], Emax = bounds[1], Xmax = bounds[2];
-    const float u = 5.9604645e-8f;  // 2^-24
-    const float etc = 8.0f * (float)kpad * u * qtn * Mmax;
-    const float E = (eq * Mmax + qn * Emax + etc) * 1.0001f;
-    const float g = 1.01f * (float)(dim + 2) * u;
-    float lb;
-    if (metric == M_IP) {
-      // d_ref(x) = -fl(q.x) >= -(q.x) - g*||q||*||x|| ;  -(q.x) >= s~ - E >= tau - E
-      lb = t - E - g * qn * Xmax;
-      lb -= fabsf(lb) * 4.0f * u;
-    } else if (metric == M_COS) {
-      // mirror rows are x/||x|| (fp32 divide, rel. error <= 2^-23 per element): -(q.x^) >= tau - E - ||q||*2^-22
-      // cos(x) = (q.x^)/||q|| <= (E' - tau)/||q||;  d_ref >= 1 - cos - (2g + 2^-21)
-      float Ep = E + qn * 4.0f * u;
-      float c = (Ep - t) / qn;
-      lb = 1.0f - c - (2.0f * g + 8.0f * u);
-      lb -= fabsf(lb) * 4.0f * u + 4.0f * u;
-      if (!(qn > 0.0f)) lb = -INF;  // zero query: every distance is exactly 1 -> ties everywhere
-    } else {
-      // ||q - x|| >= ||q~ - x~|| - ||q - q~|| - ||x - x~||, and ||q~ - x~||^2 = ||q~||^2 + s~ (s~ = ||x~||^2 - 2 q~.x~)
-      // fp32 error of s~: 2*e_tc plus the rounding of aux and of ||q~||^2 (<= K*2^-23 relative each)
-      float es = 2.0f * etc + (float)kpad * 2.0f * u * (Mmax * Mmax + qtn2);
-      float r2 = qtn2 + t - es;
-      float r = r2 > 0.0f ? sqrtf(r2) * (1.0f - 2.0f * u) : 0.0f;
-      lb = r - eq * 1.0001f - Emax;
-      lb = lb * (1.0f - g) * (1.0f - 4.0f * u);
-    }
-    ok = lb > dk;
-  }
+  const bool ok = certificate_holds(keys[(size_t)q * k + (k - 1)], tau[q], qstat[q], bounds, dim, kpad, metric);
   if (!ok) {
     uint32_t slot = atomicAdd(fail_count, 1u);
     fail_list[slot] = q;
@@ -1157,6 +1216,163 @@ __global__ void certify_kernel(const uint64_t* __restrict__ keys, const float* _
   if (counters) {
     if (counter_slot == 1) atomicAdd(counters + 0, 1ull);
     if (!ok) atomicAdd(counters + counter_slot, 1ull);
+  }
+}
+
+// ---- fused tail: merge -> exact rerank -> certificate, one block per query ----------------------------
+// What merge_candidates, rerank_kernel and certify_kernel do in three launches (each a grid of small blocks
+// plus a launch gap), for batches where those gaps are what the caller waits for: behind a 0.25 ms pass over
+// the mirror the three cost 0.04 ms, a sixth of the call. One block of 256 threads per query:
+//   1. the query's candidate keys -> shared memory; select_and_sort -> the k'' best rows and tau;
+//   2. the k'' rows are copied into shared memory by the whole block (cp.async, 16 bytes per thread and
+//      request, chunks of FIN_CHB bytes per row, two chunks in flight); thread j walks row j in the
+//      reference's sequential fp32 order (acc_step4), thread k'' the query's own norm (cosine);
+//   3. one warp sorts the k'' exact keys, thread 0 emits the first k distinct ones and checks the certificate.
+// Results are those of the three kernels bit for bit (same keys, same arithmetic, same order).
+constexpr uint32_t FIN_THREADS = 256;
+__host__ __device__ inline uint32_t fin_chunk_bytes(uint32_t kpp) { return kpp <= 32 ? 1024u : 512u; }
+__host__ __device__ inline size_t fin_smem_bytes(uint32_t n_pad, uint32_t pitch, uint32_t kpp) {
+  return (size_t)(n_pad < 256 ? 256 : n_pad) * 8 + (size_t)pitch * 4 + (size_t)2 * kpp * (fin_chunk_bytes(kpp) + 16) + 64 * 8 + (size_t)kpp * 4;
+}
+
+struct FinishArgs {
+  const float* cand_score;
+  const uint32_t* cand_row;
+  const float* chunk_tau;
+  uint32_t n_lists, kprime, n_pad, kpp;
+  const float* vec;
+  const float* norm;
+  const uint32_t* deleted;
+  uint32_t pitch, dim, n_rows, kpad;
+  const float* q;
+  const float4* qstat;
+  const float* bounds;
+  uint32_t k, row_base;
+  uint64_t* out_keys;
+  float* out_tau_chunks;
+  uint32_t* fail_list;
+  uint32_t* fail_count;
+  unsigned long long* counters;
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(FIN_THREADS) finish_queries_kernel(FinishArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_fin[];
+  const uint32_t kpp = a.kpp, CHB = fin_chunk_bytes(kpp), ROWB = CHB + 16;   // stage rows CHB + 16 bytes apart: conflict-free LDS.128
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_fin);                      // [max(n_pad, 256)]
+  float* s_q = reinterpret_cast<float*>(keys + (a.n_pad < 256 ? 256 : a.n_pad));   // [pitch]
+  unsigned char* s_stage = reinterpret_cast<unsigned char*>(s_q + a.pitch);    // [2][kpp][ROWB]
+  uint64_t* xkeys = reinterpret_cast<uint64_t*>(s_stage + (size_t)2 * kpp * ROWB);  // [64]
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(xkeys + 64);                  // [kpp]
+  __shared__ float s_red[FIN_THREADS / 32];
+  __shared__ float s_tau[2];
+  __shared__ float s_qnorm;
+  const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = a.n_lists * a.kprime;
+  const float INF = __int_as_float(0x7f800000);
+  pdl_trigger();
+  pdl_wait();
+
+  // 1. candidates, query, chunk thresholds
+  for (uint32_t i = tid; i < max(a.n_pad, 64u); i += FIN_THREADS) keys[i] = (i < n) ? candidate_key(a.cand_score, a.cand_row, (size_t)q * n + i) : KEY_NONE;
+  stage_query(s_q, a.q + (size_t)q * a.dim, a.dim, a.pitch, tid, FIN_THREADS);
+  float tmin = INF;
+  for (uint32_t c = tid; c < a.n_lists; c += FIN_THREADS) tmin = fminf(tmin, a.chunk_tau[(size_t)q * a.n_lists + c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+  if (lane == 0) s_red[warp] = tmin;
+  if (tid < 64) xkeys[tid] = KEY_NONE;
+  __syncthreads();
+  const uint32_t n_sort = select_and_sort(keys, n, a.n_pad, kpp);
+  if (tid < kpp) {
+    const uint64_t key = (tid < n_sort) ? keys[tid] : KEY_NONE;
+    uint32_t row = (key == KEY_NONE) ? ROW_NONE : (uint32_t)key;
+    if (row != ROW_NONE && (row >= a.n_rows || bit_test(a.deleted, row))) row = ROW_NONE;
+    s_rows[tid] = row;
+  }
+  if (tid == 0) {
+    float tau = INF;
+#pragma unroll
+    for (int w = 0; w < (int)(FIN_THREADS / 32); ++w) tau = fminf(tau, s_red[w]);
+    s_tau[1] = tau;  // bound on rows no chunk kept
+    if (kpp < n_sort && keys[kpp] != KEY_NONE) tau = fminf(tau, ord_f32((uint32_t)(keys[kpp] >> 32)));
+    s_tau[0] = tau;  // bound on every row that is not reranked below
+  }
+  __syncthreads();
+
+  // 2. exact distances of the k'' rows
+  const uint32_t row_bytes = a.pitch * 4, n_ch = (row_bytes + CHB - 1) / CHB, pieces = CHB / 16;
+  auto issue = [&](uint32_t ch) {
+    if (ch < n_ch) {
+      unsigned char* dst = s_stage + (size_t)(ch & 1) * kpp * ROWB;
+      for (uint32_t p = tid; p < kpp * pieces; p += FIN_THREADS) {
+        const uint32_t r = p / pieces, piece = p - r * pieces;
+        const uint32_t off = ch * CHB + piece * 16;
+        const uint32_t row = s_rows[r];
+        const bool valid = row != ROW_NONE && off < row_bytes;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vec) + (valid ? (size_t)row * row_bytes + off : 0);
+        cp_async16(dst + (size_t)r * ROWB + piece * 16, src, valid);
+      }
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  float acc = 0.0f;
+  const uint32_t my_row = tid < kpp ? s_rows[tid] : ROW_NONE;
+  const float xn = (METRIC == M_COS && my_row != ROW_NONE) ? __ldg(a.norm + my_row) : 0.0f;
+  for (uint32_t ch = 0; ch < n_ch; ++ch) {
+    cp_async_wait<1>();   // chunk ch has landed (chunk ch + 1 may still be in flight)
+    __syncthreads();
+    const uint32_t n4 = min(CHB, row_bytes - ch * CHB) / 16;
+    const float4* q4 = reinterpret_cast<const float4*>(s_q) + ch * pieces;
+    if (tid < kpp) {
+      const float4* x4 = reinterpret_cast<const float4*>(s_stage + ((size_t)(ch & 1) * kpp + tid) * ROWB);
+#pragma unroll 4
+      for (uint32_t i = 0; i < n4; ++i) acc = acc_step4<METRIC>(acc, q4[i], x4[i]);
+    } else if (METRIC == M_COS && tid == kpp) {   // the query's norm, the reference's sequential sum (distance.go:58-66)
+      for (uint32_t i = 0; i < n4; ++i) {
+        const float4 v = q4[i];
+        acc = __fadd_rn(acc, __fmul_rn(v.x, v.x));
+        acc = __fadd_rn(acc, __fmul_rn(v.y, v.y));
+        acc = __fadd_rn(acc, __fmul_rn(v.z, v.z));
+        acc = __fadd_rn(acc, __fmul_rn(v.w, v.w));
+      }
+    }
+    __syncthreads();      // buffer ch & 1 is free again
+    issue(ch + 2);
+  }
+  if (METRIC == M_COS && tid == kpp) s_qnorm = __fsqrt_rn(acc);
+  __syncthreads();
+  if (tid < kpp && my_row != ROW_NONE) xkeys[tid] = make_key(finish_distance<METRIC>(acc, METRIC == M_COS ? s_qnorm : 0.0f, xn), my_row + a.row_base);
+  __syncthreads();
+
+  // 3. order, emit, certify
+  if (warp == 0) {
+    warp_sort64(xkeys, lane);
+    __syncwarp();
+    for (uint32_t i = lane; i < a.k; i += 32) a.out_keys[(size_t)q * a.k + i] = KEY_NONE;
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t w = 0;
+      uint64_t prev = KEY_NONE, kth = KEY_NONE;
+      for (uint32_t i = 0; i < 64 && w < a.k; ++i) {   // (identical keys would be adjacent; merged candidates are distinct rows)
+        const uint64_t v = xkeys[i];
+        if (v == KEY_NONE) break;
+        if (v != prev) {
+          a.out_keys[(size_t)q * a.k + w++] = v;
+          if (w == a.k) kth = v;
+        }
+        prev = v;
+      }
+      a.out_tau_chunks[q] = s_tau[1];
+      const bool ok = certificate_holds(kth, s_tau[0], a.qstat[q], a.bounds, a.dim, a.kpad, METRIC);
+      if (!ok) a.fail_list[atomicAdd(a.fail_count, 1u)] = q;
+      if (a.counters) {
+        atomicAdd(a.counters + 0, 1ull);
+        if (!ok) atomicAdd(a.counters + 1, 1ull);
+      }
+    }
   }
 }
 
@@ -1204,18 +1420,18 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms, uint3
 }
 
 template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
-static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream) {
+static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream, bool pdl) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
                 (size_t)8 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
   SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>), smem);
-  tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN><<<grid, 64 + 128 * EW, smem, stream>>>(tmap_b, tmap_a, fa);
+  SCN_CUDA(launch_chained(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>, dim3(grid), dim3(64 + 128 * EW), smem, stream, pdl, tmap_b, tmap_a, fa));
   SCN_LAUNCHED();
   return SCN_OK;
 }
 
 static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
-                                        uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof, float* dbg_scores) {
+                                        uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof, float* dbg_scores, bool first_batch) {
   int sms = 0;
   SCN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   EncodeTiledFn enc = encode_tiled_fn();
@@ -1264,11 +1480,24 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(SCN_ERR_INTERNAL, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
+  // merge -> rerank -> certificate in one launch (finish_queries_kernel) where the launch gaps behind the filter are
+  // what the caller waits for; big batches keep the three grids (auto: up to 2048 queries)
+  const size_t fin_smem = fin_smem_bytes(n_pad, s->pitch, kpp);
+  const bool fused_tail = !dbg_scores && fin_smem <= 160 * 1024 && kpp <= 64 &&
+                          (s->opt_tensor_fused > 0 || (s->opt_tensor_fused < 0 && nq <= 2048));
+
   Scratch scratch(stream);
   __nv_bfloat16* d_qb = nullptr;
   float4* d_qstat = nullptr;
   float *d_cscore = nullptr, *d_ctau = nullptr, *d_tau = nullptr;
   uint32_t *d_crow = nullptr, *d_rows = nullptr, *d_fail = nullptr, *d_nfail = nullptr;
+  {  // one allocation for the whole call
+    const size_t sizes[] = {(size_t)nq_pad * s->kpad * 2, nq * sizeof(float4), (size_t)nq * n_cand * 4, (size_t)nq * n_cand * 4,
+                            (size_t)nq * n_lists * 4, nq * 4, (size_t)nq * kpp * 4, nq * 4, nq * 4, nq * 4, 2 * 4, nq * 4};
+    size_t total = 0;
+    for (size_t b : sizes) total += Scratch::padded(b);
+    SCN_TRY(scratch.reserve(total));
+  }
   SCN_TRY(scratch.alloc(&d_qb, (size_t)nq_pad * s->kpad));
   SCN_TRY(scratch.alloc(&d_qstat, nq));
   SCN_TRY(scratch.alloc(&d_cscore, (size_t)nq * n_cand));
@@ -1284,11 +1513,10 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(scratch.alloc(&d_nfail, 2));
   uint32_t* d_hint = nullptr;
   SCN_TRY(scratch.alloc(&d_hint, nq));
-  SCN_CUDA(cudaMemsetAsync(d_hint, 0xFF, nq * sizeof(uint32_t), stream));
-  SCN_CUDA(cudaMemsetAsync(d_nfail, 0, 2 * sizeof(uint32_t), stream));
 
   if (prof) prof->begin("prep_queries");
-  prep_queries_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(d_q, (uint32_t)nq, nq_pad, s->dim, s->kpad, d_qb, d_qstat);
+  prep_queries_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(d_q, (uint32_t)nq, nq_pad, s->dim, s->kpad, d_qb, d_qstat, d_hint, d_nfail,
+                                                            first_batch ? s->d_counters : nullptr);
   SCN_LAUNCHED();
   if (prof) prof->end();
 
@@ -1320,82 +1548,127 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   fa.hint = s->opt_tensor_hint ? d_hint : nullptr;
   fa.hint_target = (uint32_t)std::max<int64_t>(s->opt_tensor_hint_target, 0);   // 0: publish the list's own k'-th best (never costs a candidate)
   int grid = (int)std::min<uint32_t>((uint32_t)sms, n_qb * n_chunks);
+  const bool pdl = s->opt_pdl != 0 && !(prof && prof->on) && !dbg_scores;   // chained launches (common.cuh): prep -> filter -> tail
   if (prof) prof->begin("tensor_filter");
   const bool two_buf = s->kpad <= 512;
   int32_t rc;
   if (pair_kernel) {
     const int pairs = (int)std::min<uint32_t>((uint32_t)resident_pairs, ((n_qb + 1) / 2) * n_chunks);
-    if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2>(tmap, fa, pairs, stream) : launch_filter2<32, 2>(tmap, fa, pairs, stream);
-    else rc = (kprime == 16) ? launch_filter2<16, 1>(tmap, fa, pairs, stream) : launch_filter2<32, 1>(tmap, fa, pairs, stream);
+    if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 2>(tmap, fa, pairs, stream, pdl);
+    else rc = (kprime == 16) ? launch_filter2<16, 1>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 1>(tmap, fa, pairs, stream, pdl);
   } else if (stream_a) {
-    if (dbg_scores) rc = launch_filter<16, 2, 1, true, true, 128>(tmap, tmap_a, fa, grid, stream);
-    else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream)
-                             : launch_filter<32, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream);
+    if (dbg_scores) rc = launch_filter<16, 2, 1, true, true, 128>(tmap, tmap_a, fa, grid, stream, pdl);
+    else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream, pdl)
+                             : launch_filter<32, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream, pdl);
   } else if (dbg_scores) {
-    rc = two_buf ? launch_filter<16, 2, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream)
-                 : launch_filter<16, 1, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream);
+    rc = two_buf ? launch_filter<16, 2, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream, pdl)
+                 : launch_filter<16, 1, 1, true, false, 128>(tmap, tmap_a, fa, grid, stream, pdl);
   } else if (half_tiles) {
-    rc = (kprime == 16) ? launch_filter<16, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream)
-                        : launch_filter<32, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream);
+    rc = (kprime == 16) ? launch_filter<16, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream, pdl)
+                        : launch_filter<32, 2, 1, false, false, 64>(tmap, tmap_a, fa, grid, stream, pdl);
   } else if (ew == 1) {
-    rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream)
-                        : launch_filter<32, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream);
+    rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl)
+                        : launch_filter<32, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl);
   } else {
-    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream)
-                        : launch_filter<32, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream);
+    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl)
+                        : launch_filter<32, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl);
   }
   if (prof) prof->end();
   SCN_TRY(rc);
 
-  if ((size_t)n_pad * 8 > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many candidate lists (%u) for one merge block", n_lists);
-  SCN_ALLOW_SMEM((merge_candidates_kernel), ((size_t)n_pad * 8));
-  if (prof) prof->begin("merge_candidates");
-  // one block per query; long candidate lists (small batches: many chunks) get more threads per sort
-  merge_candidates_kernel<<<(unsigned)nq, std::min(512u, std::max(128u, n_pad / 4)), (size_t)n_pad * 8, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime, n_pad, kpp,
-                                                                            d_rows, d_tau, d_tau_chunks);
-  SCN_LAUNCHED();
-  if (prof) prof->end();
+  if (fused_tail) {
+    FinishArgs fin;
+    fin.cand_score = d_cscore;
+    fin.cand_row = d_crow;
+    fin.chunk_tau = d_ctau;
+    fin.n_lists = n_lists;
+    fin.kprime = kprime;
+    fin.n_pad = n_pad;
+    fin.kpp = kpp;
+    fin.vec = s->d_vec;
+    fin.norm = s->d_norm;
+    fin.deleted = s->d_deleted;
+    fin.pitch = s->pitch;
+    fin.dim = s->dim;
+    fin.n_rows = n_rows;
+    fin.kpad = s->kpad;
+    fin.q = d_q;
+    fin.qstat = d_qstat;
+    fin.bounds = s->d_bounds;
+    fin.k = k;
+    fin.row_base = (uint32_t)row_base;
+    fin.out_keys = d_out_keys;
+    fin.out_tau_chunks = d_tau_chunks;
+    fin.fail_list = d_fail;
+    fin.fail_count = d_nfail;
+    fin.counters = s->d_counters;
+    if (prof) prof->begin("finish_queries");
+#define FIN(MT)                                                                              \
+  do {                                                                                       \
+    SCN_ALLOW_SMEM((finish_queries_kernel<MT>), fin_smem);                                   \
+    SCN_CUDA(launch_chained(finish_queries_kernel<MT>, dim3((unsigned)nq), dim3(FIN_THREADS), fin_smem, stream, pdl, fin)); \
+  } while (0)
+    switch (s->metric) {
+      case M_L2: FIN(M_L2); break;
+      case M_COS: FIN(M_COS); break;
+      default: FIN(M_IP); break;
+    }
+#undef FIN
+    SCN_LAUNCHED();
+    if (prof) prof->end();
+  } else {
+    const size_t merge_smem = (size_t)std::max(n_pad, 256u) * 8;
+    if (merge_smem > 200 * 1024) return fail(SCN_ERR_INVALID_PARAMETERS, "too many candidate lists (%u) for one merge block", n_lists);
+    SCN_ALLOW_SMEM((merge_candidates_kernel), merge_smem);
+    if (prof) prof->begin("merge_candidates");
+    // one block per query; long candidate lists (small batches: many chunks) get more threads per sort
+    merge_candidates_kernel<<<(unsigned)nq, std::min(512u, std::max(128u, n_pad / 4)), merge_smem, stream>>>(d_cscore, d_crow, d_ctau, n_lists, kprime,
+                                                                                                              n_pad, kpp, d_rows, d_tau, d_tau_chunks);
+    SCN_LAUNCHED();
+    if (prof) prof->end();
 
-  if (prof) prof->begin("rerank_exact");
-  SCN_TRY(rerank_rows(s, d_q, nq, d_rows, kpp, k, row_base, d_out_keys, stream));
-  if (prof) prof->end();
+    if (prof) prof->begin("rerank_exact");
+    SCN_TRY(rerank_rows(s, d_q, nq, d_rows, kpp, k, row_base, d_out_keys, stream));
+    if (prof) prof->end();
 
-  if (prof) prof->begin("certify");
-  certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau, d_qstat, s->d_bounds, (uint32_t)nq, k, s->dim,
-                                                                   s->kpad, s->metric, nullptr, nullptr, d_fail, d_nfail,
-                                                                   s->d_counters, 1);
-  SCN_LAUNCHED();
-  if (prof) prof->end();
+    if (prof) prof->begin("certify");
+    certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau, d_qstat, s->d_bounds, (uint32_t)nq, k, s->dim,
+                                                                     s->kpad, s->metric, nullptr, nullptr, d_fail, d_nfail,
+                                                                     s->d_counters, 1);
+    SCN_LAUNCHED();
+    if (prof) prof->end();
+  }
 
   // second chance for the few queries whose k'' rows were not enough: rerank every candidate the
   // chunks kept (n_chunks * k') and certify against the chunk thresholds alone
+  const uint32_t* d_nfail_final = d_nfail + 1;
   if (n_cand > kpp) {
     if (prof) prof->begin("rerank_exact_wide");
     SCN_TRY(rerank_rows(s, d_q, nq, d_crow, n_cand, k, row_base, d_out_keys, stream, d_fail, d_nfail));
     if (prof) prof->end();
     if (prof) prof->begin("certify_wide");
-    certify_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_out_keys, d_tau_chunks, d_qstat, s->d_bounds, (uint32_t)nq, k,
-                                                                     s->dim, s->kpad, s->metric, d_fail, d_nfail, d_fail2,
-                                                                     d_nfail + 1, s->d_counters, 2);
+    SCN_CUDA(launch_chained(certify_kernel, dim3((unsigned)((nq + 127) / 128)), dim3(128), 0, stream, pdl, (const uint64_t*)d_out_keys,
+                            (const float*)d_tau_chunks, (const float4*)d_qstat, (const float*)s->d_bounds, (uint32_t)nq, k, s->dim, s->kpad,
+                            (int)s->metric, (const uint32_t*)d_fail, (const uint32_t*)d_nfail, d_fail2, d_nfail + 1, s->d_counters, 2));
     SCN_LAUNCHED();
     if (prof) prof->end();
   } else {
-    d_fail2 = d_fail;  // nothing wider to look at
-    SCN_CUDA(cudaMemcpyAsync(d_nfail + 1, d_nfail, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+    d_fail2 = d_fail;  // nothing wider to look at: the first list of failures is the final one
+    d_nfail_final = d_nfail;
   }
 
   // exact scan for whatever could still not be certified (normally nothing: the kernel exits at once)
-  return flat_search_exact(s, d_q, d_fail2, d_nfail + 1, nq, k, row_base, d_out_keys, stream, prof);
+  return flat_search_exact(s, d_q, d_fail2, d_nfail_final, nq, k, row_base, d_out_keys, stream, prof);
 }
 
 int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys,
                            cudaStream_t stream, Profiler* prof) {
-  SCN_CUDA(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), stream));
+  // (the device counters are cleared by the first batch's prep_queries)
   // bound the scratch of the (normally idle) exact fallback: sms * nq * k * 8 bytes of partial lists
   const uint64_t max_batch = std::max<uint64_t>(1024, (512ull << 20) / ((uint64_t)160 * k * 8));
   for (uint64_t q0 = 0; q0 < nq; q0 += max_batch) {
     uint64_t n = std::min(max_batch, nq - q0);
-    SCN_TRY(flat_search_tensor_batch(s, d_q + q0 * s->dim, n, k, row_base, d_out_keys + q0 * k, stream, prof, nullptr));
+    SCN_TRY(flat_search_tensor_batch(s, d_q + q0 * s->dim, n, k, row_base, d_out_keys + q0 * k, stream, prof, nullptr, q0 == 0));
   }
   return SCN_OK;
 }
@@ -1404,7 +1677,7 @@ int32_t tensor_debug_scores(scn_store* s, const float* d_q, uint64_t nq, float* 
   Scratch scratch(stream);
   uint64_t* d_keys = nullptr;
   SCN_TRY(scratch.alloc(&d_keys, nq * 10));
-  return flat_search_tensor_batch(s, d_q, nq, 10, 0, d_keys, stream, nullptr, d_scores);
+  return flat_search_tensor_batch(s, d_q, nq, 10, 0, d_keys, stream, nullptr, d_scores, true);
 }
 
 int32_t mark_aux_deleted(scn_store* s, const uint32_t* h_rows, uint32_t n, cudaStream_t stream) {

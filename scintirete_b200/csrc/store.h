@@ -83,6 +83,8 @@ struct scn_store {
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
   int64_t opt_tensor_pair = 1;    // 1 = CTA-pair filter kernel (cta_group::2, M=256 x N=128, queries stationary in TMEM) at kpad 512 / 640 / 768, batches >= 256
+  int64_t opt_tensor_fused = -1;  // merge -> exact rerank -> certificate behind the filter in ONE launch (finish_queries_kernel): 1 always, 0 never, -1 auto (batches of up to 2048 queries)
+  int64_t opt_pdl = 1;            // the short kernels behind the tensor filter are launched chained (programmatic dependent launch, common.cuh)
   int64_t opt_build_window = 0;   // scn_hnsw_insert: inserts searched speculatively per round; 0 = adaptive, 1 = none (serial)
   int64_t opt_profile = 0;
 
@@ -128,9 +130,33 @@ struct DeviceGuard {
 struct Scratch {
   cudaStream_t stream;
   std::vector<void*> ptrs;
+  char* pool = nullptr;        // one block reserved up front (reserve()): later allocs are carved out of it
+  size_t pool_bytes = 0, pool_used = 0;
   explicit Scratch(cudaStream_t s) : stream(s) {}
+  static size_t padded(size_t bytes) { return (bytes + 16 + 255) & ~(size_t)255; }
+  // One stream-ordered allocation for a whole call instead of one per buffer (a call of the tensor path
+  // needs about fifteen): `bytes` = sum of padded(size) over the buffers that will follow.
+  int32_t reserve(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return scn::fail(SCN_ERR_RESOURCE, "device scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ptrs.push_back(p);
+    pool = static_cast<char*>(p);
+    pool_bytes = bytes;
+    pool_used = 0;
+    return SCN_OK;
+  }
   template <class T>
   int32_t alloc(T** out, size_t count) {
+    const size_t need = padded(count * sizeof(T));
+    if (pool && pool_used + need <= pool_bytes) {
+      *out = reinterpret_cast<T*>(pool + pool_used);
+      pool_used += need;
+      return SCN_OK;
+    }
     void* p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, count * sizeof(T) + 16, stream);
     if (e != cudaSuccess) {
@@ -196,7 +222,7 @@ int32_t flat_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlis
                           uint64_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_keys, cudaStream_t stream,
                           Profiler* prof);
 int32_t keys_to_results(scn_store* s, const uint64_t* d_keys, uint64_t n, uint64_t row_base, uint64_t* d_out_ids,
-                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream);
+                        float* d_out_dist, uint32_t* d_out_counts, uint32_t k, cudaStream_t stream, bool chained = false);
 int32_t flat_search_tensor(scn_store* s, const float* d_q, uint64_t nq, uint32_t k, uint64_t row_base,
                            uint64_t* d_out_keys, cudaStream_t stream, Profiler* prof);
 bool tensor_path_supported(const scn_store* s, uint32_t k);

@@ -210,3 +210,57 @@ def test_cta_pair_filter_equals_oracle(metric, n, d, nq, k):
     o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, deleted=deleted, nthreads=8)
     assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt)
     s.close()
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 768, 5, 10), (6000, 128, 130, 10), (9999, 200, 1, 1), (5000, 64, 129, 24),
+                                      (9000, 1536, 40, 10), (5000, 1000, 33, 10), (4200, 33, 17, 10), (150000, 96, 3, 10)])
+def test_fused_tail_equals_three_kernel_tail_and_oracle(metric, n, d, nq, k):
+    # finish_queries_kernel (candidate merge + exact rerank + certificate in one launch, option tensor_fused) against
+    # merge_candidates -> rerank -> certify and against the oracle: ids, distance bits, counts, and the same
+    # certificate decisions (counters). Covers one query, ragged dims, k'' = 64 (rows > 768 elements), k' = 32,
+    # deleted rows, a duplicated row, and long candidate lists (few queries over many row chunks: radix select).
+    db, q = gaussian(n, d, 77), gaussian(nq, d, 78)
+    db[n - 1] = db[7]
+    q[0] = db[7]
+    s = DeviceStore(d, metric)
+    s.append(db)
+    dead = np.array([3, n // 2, n - 2], np.uint64)
+    s.mark_deleted(dead)
+    deleted = np.zeros(n, np.uint8)
+    deleted[dead.astype(np.int64) - 1] = 1
+    s.set_option("flat_path", 2)
+    s.set_option("profile", 1)
+    got = {}
+    for fused in (0, 1):
+        s.set_option("tensor_fused", fused)
+        s.last_timings()
+        ids, dist, cnt = s.search_flat(q, k)
+        names = s.last_timings()
+        assert ("finish_queries" in names) == bool(fused) and ("merge_candidates" in names) != bool(fused), names
+        got[fused] = (ids, dist, cnt, s.last_counters()[:3])
+    s.close()
+    o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, deleted=deleted, nthreads=8)
+    for fused in (0, 1):
+        ids, dist, cnt, _ = got[fused]
+        assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt), fused
+    assert got[0][3][0] == got[1][3][0] == nq
+
+
+def test_fused_tail_with_ties_everywhere():
+    # all rows identical: every filter score ties, no certificate can hold, every query ends in the exact scan —
+    # through the fused tail exactly as through the three kernels
+    n, d, nq, k = 5000, 128, 9, 10
+    db = np.tile(gaussian(1, d, 5), (n, 1))
+    q = gaussian(nq, d, 6)
+    for fused in (0, 1):
+        s = DeviceStore(d, DistanceMetric.L2)
+        s.append(db)
+        s.set_option("flat_path", 2)
+        s.set_option("tensor_fused", fused)
+        ids, dist, cnt = s.search_flat(q, k)
+        rescanned = s.last_counters()[2]
+        s.close()
+        o = oracle.flat_search(1, db, q, k, nthreads=8)
+        assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1]) and np.array_equal(cnt, o[2])
+        assert rescanned == nq
