@@ -136,6 +136,9 @@ struct FilterArgs {
   float* dbg_scores;        // optional [nq][n_rows]
   uint32_t* hint;           // [nq] ord(lowest threshold published by a finished list of the query), 0xFFFFFFFF = none
   uint32_t hint_target;     // rows of the whole shard that should beat a published threshold (see publish_value)
+  float* pub;               // optional float2 [lists_pad][nq_stride]: the two best scores every list of a query has found so far (see publish_two_best)
+  uint32_t lists_pad;       // lists per query in `pub`, rounded up to 16 (never-written entries stay NaN)
+  uint32_t nq_stride;       // queries per list row of `pub` (whole query blocks)
 };
 
 
@@ -195,8 +198,92 @@ __device__ __forceinline__ float publish_value(const float (&sc)[KP], uint32_t r
   return pub;   // +Inf when the list holds fewer than j rows
 }
 
+// Thresholds shared between the lists of a query WHILE they are being built. With few queries a query block is
+// spread over dozens of row chunks that all start at the same time: every list converges on its own from +Inf
+// (k' ln(rows / k') insertions), and because a warp gates 32 queries at once, almost every 16-column segment of
+// such a list takes the insertion path — the filter of 256..1024 queries ran at half the rate its MMAs allow.
+// Each list therefore publishes its two best scores whenever they may have changed (`pub`: one float2 per list
+// and query, [lists_pad][nq_stride], so that the 32 queries of a warp store / load one 256-byte segment), and
+// ONE extra warp per CTA — the bound helper, which has nothing else to do — keeps turning the table into a
+// bound per query of the block the CTA is working on: list l feeds groups (l mod 16, rank) — 32 groups, each
+// holding the score of a row of its own (a row belongs to one list, and the two best of a list are two rows).
+// B = the maximum over the groups of the group minimum: 32 distinct rows score <= B, so the query's 32nd best
+// score over the whole shard is <= B, and rows that score >= B cannot be among the k'' = 32 rows the rerank gets:
+// B is an admissible threshold for every list of the query, and no theta ever drops below the final 32nd best
+// score, which is (within one rank) the tau the certificate works with anyway. The helper leaves (item, B) pairs
+// in shared memory (one 8-byte store each); an epilogue lane takes a bound only if it carries the item the lane
+// is working on. Everything is racy on purpose: a value that was ever published stays the score of an existing
+// row. Fewer than 16 lists: some group stays empty, B = +Inf.
+template <int KP>
+__device__ __forceinline__ void publish_two_best(const float (&sc)[KP], float* dst) {
+  const float INF = __int_as_float(0x7f800000);
+  float m1 = sc[0];
+#pragma unroll
+  for (int j = 1; j < KP; ++j) m1 = fminf(m1, sc[j]);
+  float m2 = INF;   // (equal scores of two rows count twice)
+  bool skipped = false;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    const bool skip = !skipped && sc[j] == m1;
+    m2 = skip ? m2 : fminf(m2, sc[j]);
+    skipped = skipped || skip;
+  }
+  asm volatile("st.global.cg.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(m1), "f"(m2) : "memory");
+}
+constexpr uint32_t ITEM_NONE = 0xFFFFFFFEu, ITEM_EXIT = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t ld_shared_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// the (item, bound) pair of a query row of the block; +Inf unless it belongs to `item`
+__device__ __forceinline__ float helper_bound_for(const uint2* s_hb, uint32_t qrow, uint32_t item) {
+  uint32_t tag, bits;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tag), "=r"(bits) : "r"(smem_u32(s_hb + qrow)) : "memory");
+  return tag == item ? __uint_as_float(bits) : __int_as_float(0x7f800000);
+}
+// The helper warp: until the CTA has finished its last item, bounds for the 128 queries starting at q0(item).
+template <class ItemToQuery>
+__device__ __forceinline__ void bound_helper_loop(const FilterArgs& a, const uint32_t* s_cur_item, uint2* s_hb, uint32_t lane, ItemToQuery q0_of) {
+  const float INF = __int_as_float(0x7f800000);
+  for (;;) {
+    const uint32_t item = ld_shared_volatile_u32(s_cur_item);
+    if (item == ITEM_EXIT) break;
+    if (item == ITEM_NONE) {
+      __nanosleep(500);
+      continue;
+    }
+    const uint32_t q0 = q0_of(item);
+    for (uint32_t r = 0; r < 4; ++r) {
+      const float2* src = reinterpret_cast<const float2*>(a.pub) + (q0 + r * 32 + lane);   // (< nq_stride: the table is padded to whole blocks)
+      float g0[16], g1[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) g0[u] = g1[u] = INF;
+      for (uint32_t l0 = 0; l0 < a.lists_pad; l0 += 16) {
+        float2 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v[u].x), "=f"(v[u].y) : "l"(src + (size_t)(l0 + u) * a.nq_stride));
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {   // fminf drops the NaN of entries nobody has written yet
+          g0[u] = fminf(g0[u], v[u].x);
+          g1[u] = fminf(g1[u], v[u].y);
+        }
+      }
+      float bound = fmaxf(g0[0], g1[0]);
+#pragma unroll
+      for (int u = 1; u < 16; ++u) bound = fmaxf(bound, fmaxf(g0[u], g1[u]));
+      asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_u32(s_hb + r * 32 + lane)), "r"(item), "r"(__float_as_uint(bound)) : "memory");
+    }
+    __nanosleep(1000);
+  }
+}
+
 template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
-__global__ void __launch_bounds__(64 + 128 * EW, 1)
+__global__ void __launch_bounds__(96 + 128 * EW, 1)
     tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a, FilterArgs a) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   constexpr int TF_BN = BN;
@@ -220,12 +307,16 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
   uint64_t* acc_full = empty + TF_STAGES;    // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;        // [2]       epilogue -> MMA
   uint64_t* a_ready = acc_empty + 2;         // [1]       epilogue (A stored) -> MMA
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint2* s_hb = reinterpret_cast<uint2*>(a_ready + 1);            // [128] (item, bound) per query row, written by the bound helper
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_hb + 128);
+  uint32_t* s_cur_item = s_tmem + 1;                              // the item the epilogue is working on (for the bound helper)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t KB = a.kpad / KSTEP;   // stages per tile
 
+  if (threadIdx.x < 128) s_hb[threadIdx.x] = make_uint2(ITEM_NONE, 0x7f800000u);
   if (threadIdx.x == 0) {
+    *s_cur_item = ITEM_NONE;
     for (int i = 0; i < TF_STAGES; ++i) {
       mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
@@ -327,6 +418,12 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
         }
       }
     }
+  } else if (warp == 2 + 4 * EW) {
+    // ===== bound helper (see publish_two_best) =====
+    if (a.pub) {
+      pdl_wait();   // the table is initialised by prep_queries
+      bound_helper_loop(a, s_cur_item, s_hb, (uint32_t)lane, [&](uint32_t item) { return (item % a.n_qblocks) * (uint32_t)TF_BM; });
+    }
   } else {
     // ===== epilogue warps: thread <-> query (TMEM lane) =====
     const uint32_t quarter = warp & 3;                 // TMEM lane quarter this warp may access
@@ -386,6 +483,10 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       }
       float theta = hint;  // min(hint, max of sc[]): the threshold every admitted row must beat
       int imax = 0;        // a slot holding theta
+      const bool sharing = a.pub != nullptr;   // (see publish_two_best)
+      float* my_pub = a.pub + ((size_t)(chunk * EW + slice) * a.nq_stride + q_global) * 2;   // (q_global < nq_stride)
+      bool dirty = false;                      // the list changed since it was last published
+      if (sharing && warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, item);
       // additive per-column term for the first tile, fetched one tile ahead from here on
       // Each warp stages the term of its own CW columns (lanes 0..CW/4-1, one float4 each) in a
       // private double buffer: no block barrier per tile, so the epilogue warps are coupled only
@@ -498,6 +599,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
                 }
                 theta = fminf(mv[0], hint);
                 imax = mi[0];
+                dirty = true;
               }
             }
           }
@@ -513,6 +615,14 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
             if (c < a.n_rows) a.dbg_scores[(size_t)q_global * a.n_rows + c] = v[j];
           }
         }
+        if (sharing) {   // what the list found goes out, what the helper made of everybody's lists comes in
+          if (dirty && ((t - t0) & 1u)) {
+            publish_two_best<KP>(sc, my_pub);
+            dirty = false;
+          }
+          hint = fminf(hint, helper_bound_for(s_hb, qrow, item));
+          theta = fminf(theta, hint);
+        }
       }
       // ---- chunk result ----
       if (q_global < a.nq) {
@@ -525,6 +635,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
           a.cand_row[base + j] = my_row[j * ET];
         }
         a.chunk_tau[(size_t)q_global * a.n_chunks * EW + vchunk] = theta;
+        if (sharing) publish_two_best<KP>(sc, my_pub);   // the list's final two best, for the lists of later waves
         if (a.hint) {
           const float pub = a.hint_target == 0 ? theta
                                                : fminf(theta, publish_value<KP>(sc, (min(a.n_rows, t1 * (uint32_t)TF_BN) - t0 * (uint32_t)TF_BN) / EW,
@@ -534,6 +645,7 @@ __global__ void __launch_bounds__(64 + 128 * EW, 1)
       }
       // all MMAs of this item have retired (the last acc_full was waited on), so A may be rewritten
     }
+    if (warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, ITEM_EXIT);   // releases the bound helper
   }
 
   tc_fence_before();
@@ -613,7 +725,7 @@ __device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem,
 
 // NBUF: accumulators per CTA — 2 when the A operand leaves room (kpad <= 512), else 1
 template <int KP, int NBUF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
     tensor_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -628,7 +740,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   uint64_t* acc_full = empty + TF2_STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint64_t* a_ready = acc_empty + 2;           // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint2* s_hb = reinterpret_cast<uint2*>(a_ready + 1);            // [128] (item, bound) per query row, written by the bound helper (warp 6)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_hb + 128);
+  uint32_t* s_cur_item = s_tmem + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();     // 0 = leader (issues the MMAs)
@@ -637,7 +751,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const uint32_t n_items = n_pairs * a.n_chunks;
   const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
+  if (threadIdx.x < 128) s_hb[threadIdx.x] = make_uint2(ITEM_NONE, 0x7f800000u);
   if (threadIdx.x == 0) {
+    *s_cur_item = ITEM_NONE;
     for (int i = 0; i < TF2_STAGES; ++i) {
       mbar_init(full + i, 2);                  // one arrive per CTA of the pair (+ the transaction bytes of both)
       mbar_init(empty + i, 1);
@@ -734,6 +850,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
         }
       }
     }
+  } else if (warp == 6) {
+    // ===== bound helper (see publish_two_best): the 128 queries of THIS CTA =====
+    if (a.pub) {
+      pdl_wait();   // the table is initialised by prep_queries
+      bound_helper_loop(a, s_cur_item, s_hb, (uint32_t)lane, [&](uint32_t item) { return ((item % n_pairs) * 2 + rank) * (uint32_t)TF_BM; });
+    }
   } else {
     // ===== epilogue warps: thread <-> query (TMEM lane of this CTA) =====
     const uint32_t quarter = warp & 3;
@@ -786,6 +908,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
       float theta = hint;
       int imax = 0;
+      const bool sharing = a.pub != nullptr;   // (see publish_two_best)
+      float* my_pub = a.pub + ((size_t)chunk * a.nq_stride + q_global) * 2;   // (q_global < nq_stride)
+      bool dirty = false;                      // the list changed since it was last published
+      if (sharing && warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, item);
       // additive term of the 128 columns of a tile: one float4 per lane, fetched one tile ahead
       auto load_aux = [&](uint32_t t) -> float4 {
         float4 r = make_float4(INF, INF, INF, INF);
@@ -874,9 +1000,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
                 }
                 theta = fminf(mv[0], hint);
                 imax = mi[0];
+                dirty = true;
               }
             }
           }
+        }
+        if (sharing) {   // what the list found goes out, what the helper made of everybody's lists comes in
+          if (dirty && ((t - t0) & 1u)) {
+            publish_two_best<KP>(sc, my_pub);
+            dirty = false;
+          }
+          hint = fminf(hint, helper_bound_for(s_hb, qrow, item));
+          theta = fminf(theta, hint);
         }
       }
       // ---- chunk result: one candidate list per (query, chunk) ----
@@ -888,6 +1023,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
           a.cand_row[base + j] = my_row[j * ET];
         }
         a.chunk_tau[(size_t)q_global * a.n_chunks + chunk] = theta;
+        if (sharing) publish_two_best<KP>(sc, my_pub);   // the list's final two best, for the lists of later waves
         if (a.hint) {
           const float pub = a.hint_target == 0 ? theta
                                                : fminf(theta, publish_value<KP>(sc, min(a.n_rows, t1 * (uint32_t)TF2_BN) - t0 * (uint32_t)TF2_BN,
@@ -896,6 +1032,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
         }
       }
     }
+    if (warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, ITEM_EXIT);   // releases the bound helper
   }
 
   tc_fence_before();
@@ -910,7 +1047,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 template <int KP>
 static size_t filter2_smem() {
   return 1024 + (size_t)TF2_STAGES * TF2_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 + (size_t)4 * 2 * TF2_BN * 4 +
-         (size_t)(2 * TF2_STAGES + 5) * 8 + 16;
+         (size_t)(2 * TF2_STAGES + 5) * 8 + 128 * 8 + 16;
 }
 
 // CTA pairs that are resident at the same time (not every SM of the part has a free partner in its
@@ -922,7 +1059,7 @@ static int32_t filter2_resident_pairs(int* out) {
     SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, 1>), filter2_smem<KP>());
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * 74);
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(224);
     cfg.dynamicSmemBytes = filter2_smem<KP>();
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, tensor_filter2_kernel<KP, 1>, &cfg) != cudaSuccess || n < 1) {
@@ -939,7 +1076,7 @@ static int32_t filter2_resident_pairs(int* out) {
 template <int KP, int NBUF>
 static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, int pairs, cudaStream_t stream, bool pdl) {
   SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, NBUF>), filter2_smem<KP>());
-  SCN_CUDA(launch_chained(tensor_filter2_kernel<KP, NBUF>, dim3(2 * pairs), dim3(192), filter2_smem<KP>(), stream, pdl, tmap_b, fa));   // (cluster dims are compiled in)
+  SCN_CUDA(launch_chained(tensor_filter2_kernel<KP, NBUF>, dim3(2 * pairs), dim3(224), filter2_smem<KP>(), stream, pdl, tmap_b, fa));   // (cluster dims are compiled in)
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -952,7 +1089,8 @@ static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, i
 __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t nq_pad, uint32_t dim,
                                                            uint32_t kpad, __nv_bfloat16* __restrict__ qb,
                                                            float4* __restrict__ qstat, uint32_t* __restrict__ hint,
-                                                           uint32_t* __restrict__ nfail, unsigned long long* __restrict__ counters) {
+                                                           uint32_t* __restrict__ nfail, unsigned long long* __restrict__ counters,
+                                                           float* __restrict__ pub, uint32_t lists_pad) {
   uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_trigger();   // the filter may set itself up (barriers, TMEM, first row tiles) while the queries are converted
@@ -980,6 +1118,9 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
     qstat[qi] = make_float4(sqrtf(nn), sqrtf(mm), sqrtf(ee), mm);
     hint[qi] = 0xFFFFFFFFu;
   }
+  if (pub)   // the table of published bests, float2 [lists_pad][nq_pad]: NaN = nothing published yet
+    for (uint32_t l = lane; l < lists_pad; l += 32)
+      reinterpret_cast<float2*>(pub)[(size_t)l * nq_pad + qi] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
 }
 
 // ---- candidate merge: chunk lists -> k'' rows + tau -------------------------------------------------
@@ -1423,9 +1564,9 @@ template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
 static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream, bool pdl) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
-                (size_t)8 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 16;
+                (size_t)8 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 128 * 8 + 16;
   SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>), smem);
-  SCN_CUDA(launch_chained(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>, dim3(grid), dim3(64 + 128 * EW), smem, stream, pdl, tmap_b, tmap_a, fa));
+  SCN_CUDA(launch_chained(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>, dim3(grid), dim3(96 + 128 * EW), smem, stream, pdl, tmap_b, tmap_a, fa));
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -1486,14 +1627,20 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   const bool fused_tail = !dbg_scores && fin_smem <= 160 * 1024 && kpp <= 64 &&
                           (s->opt_tensor_fused > 0 || (s->opt_tensor_fused < 0 && nq <= 2048));
 
+  // lists of a query exchange bounds while they are built (publish_two_best) when there are at least 16 of them — few
+  // queries spread over many row chunks; the deep cut of wide rows (k'' = 64) keeps its own, looser thresholds
+  const uint32_t lists_pad = (n_lists + 15) / 16 * 16;
+  const bool share = s->opt_tensor_share != 0 && n_lists >= 16 && !stream_a && !dbg_scores;
+
   Scratch scratch(stream);
   __nv_bfloat16* d_qb = nullptr;
   float4* d_qstat = nullptr;
-  float *d_cscore = nullptr, *d_ctau = nullptr, *d_tau = nullptr;
+  float *d_cscore = nullptr, *d_ctau = nullptr, *d_tau = nullptr, *d_pub = nullptr;
   uint32_t *d_crow = nullptr, *d_rows = nullptr, *d_fail = nullptr, *d_nfail = nullptr;
   {  // one allocation for the whole call
     const size_t sizes[] = {(size_t)nq_pad * s->kpad * 2, nq * sizeof(float4), (size_t)nq * n_cand * 4, (size_t)nq * n_cand * 4,
-                            (size_t)nq * n_lists * 4, nq * 4, (size_t)nq * kpp * 4, nq * 4, nq * 4, nq * 4, 2 * 4, nq * 4};
+                            (size_t)nq * n_lists * 4, nq * 4, (size_t)nq * kpp * 4, nq * 4, nq * 4, nq * 4, 2 * 4, nq * 4,
+                            share ? (size_t)nq_pad * lists_pad * 8 : 0};
     size_t total = 0;
     for (size_t b : sizes) total += Scratch::padded(b);
     SCN_TRY(scratch.reserve(total));
@@ -1513,10 +1660,11 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   SCN_TRY(scratch.alloc(&d_nfail, 2));
   uint32_t* d_hint = nullptr;
   SCN_TRY(scratch.alloc(&d_hint, nq));
+  if (share) SCN_TRY(scratch.alloc(&d_pub, (size_t)nq_pad * lists_pad * 2));
 
   if (prof) prof->begin("prep_queries");
   prep_queries_kernel<<<(nq_pad + 3) / 4, 128, 0, stream>>>(d_q, (uint32_t)nq, nq_pad, s->dim, s->kpad, d_qb, d_qstat, d_hint, d_nfail,
-                                                            first_batch ? s->d_counters : nullptr);
+                                                            first_batch ? s->d_counters : nullptr, d_pub, lists_pad);
   SCN_LAUNCHED();
   if (prof) prof->end();
 
@@ -1547,6 +1695,9 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   fa.dbg_scores = dbg_scores;
   fa.hint = s->opt_tensor_hint ? d_hint : nullptr;
   fa.hint_target = (uint32_t)std::max<int64_t>(s->opt_tensor_hint_target, 0);   // 0: publish the list's own k'-th best (never costs a candidate)
+  fa.pub = d_pub;
+  fa.lists_pad = lists_pad;
+  fa.nq_stride = nq_pad;
   int grid = (int)std::min<uint32_t>((uint32_t)sms, n_qb * n_chunks);
   const bool pdl = s->opt_pdl != 0 && !(prof && prof->on) && !dbg_scores;   // chained launches (common.cuh): prep -> filter -> tail
   if (prof) prof->begin("tensor_filter");

@@ -264,3 +264,23 @@ def test_fused_tail_with_ties_everywhere():
         o = oracle.flat_search(1, db, q, k, nthreads=8)
         assert np.array_equal(ids, o[0]) and np.array_equal(dist, o[1]) and np.array_equal(cnt, o[2])
         assert rescanned == nq
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("n,d,nq,k", [(150000, 96, 3, 10), (60000, 512, 256, 10), (100000, 768, 300, 10), (40000, 200, 130, 24)])
+def test_shared_bounds_between_lists_keep_results_and_certificates(metric, n, d, nq, k):
+    # few queries over many row chunks: >= 16 candidate lists per query exchange bounds while they are built
+    # (shared_bound, option tensor_share) — both filter kernels. Results stay the oracle's bit for bit, and the
+    # tighter thresholds do not cost certificates (a bound never drops below the query's 32nd best score).
+    db, q = gaussian(n, d, 91), gaussian(nq, d, 92)
+    s = DeviceStore(d, metric)
+    s.append(db)
+    s.set_option("flat_path", 2)
+    o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, nthreads=8)
+    for share in (1, 0):
+        s.set_option("tensor_share", share)
+        ids, dist, cnt = s.search_flat(q, k)
+        tensor_q, widened, rescanned = s.last_counters()[:3]
+        assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt), share
+        assert tensor_q == nq and widened <= 0.02 * nq + 1 and rescanned <= widened, (share, widened, rescanned)
+    s.close()
