@@ -336,8 +336,11 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *                       batches of >= 256 queries (default), 0 = the single-CTA kernel everywhere
  *   "tensor_fused"      candidate merge, exact rerank and certificate behind the filter in one launch per batch
  *                       (one block per query): 1 always, 0 never (three grids), -1 auto (batches of <= 2048 queries)
- *   "tensor_share"      1 = the candidate lists of a query exchange bounds while the filter builds them (used when a
- *                       query has >= 16 lists: up to about a thousand queries over a large store), 0 = every list on its own
+ *   "tensor_pair_ew"    pair kernel: epilogue warps per TMEM lane quarter (each gates 128 / n columns of a tile into its own
+ *                       list): 0 = auto (2), 1, 2
+ *   "tensor_share"      1 = the candidate lists of a query exchange bounds while the filter builds them where that pays (rows of
+ *                       <= 256 elements, >= 16 lists per query, at most two waves of work items), 2 = whenever a query has
+ *                       >= 16 lists, 0 = every list on its own
  *   "pdl"               1 = the short kernels behind the tensor filter are launched chained (programmatic dependent
  *                       launch: the start-up of a kernel overlaps the kernel before it), 0 = ordinary launches
  *   "hnsw_gather"       row gather of hnsw_search: -1 auto, 0 registers (LDG.256), 1 / 2 / 3 shared-memory

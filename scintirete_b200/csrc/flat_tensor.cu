@@ -278,7 +278,7 @@ __device__ __forceinline__ void bound_helper_loop(const FilterArgs& a, const uin
       for (int u = 1; u < 16; ++u) bound = fmaxf(bound, fmaxf(g0[u], g1[u]));
       asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_u32(s_hb + r * 32 + lane)), "r"(item), "r"(__float_as_uint(bound)) : "memory");
     }
-    __nanosleep(1000);
+    __nanosleep(3000);
   }
 }
 
@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(96 + 128 * EW, 1)
 //                           wait for this, ~15 % of a tile; the gate itself overlaps the next tile)
 //              a_ready      leader CTA only; both CTAs' epilogue warps arrive after storing A
 // The epilogue is the one above (threshold gate, k' best per query and chunk).
-constexpr int TF2_STAGES = 10;                             // 16 KB each: 64 rows x 128 K bf16 (two 64-K boxes)
+// stages of 16 KB each (64 rows x 128 K bf16, two 64-K boxes): what fits 227 KB next to the lists and queues
+__host__ __device__ constexpr int filter2_stages(int kp, int ew) { return (ew == 2 && kp > 16) ? 9 : 10; }
 constexpr int TF2_STAGE_BYTES = 64 * 128 * 2;
 constexpr int TF2_BN = 128;                                // rows per pair tile (UMMA N); 64 loaded per CTA
 constexpr int TF2_KSTEP = 128;
@@ -724,23 +725,30 @@ __device__ __forceinline__ void tc_mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem,
 }
 
 // NBUF: accumulators per CTA — 2 when the A operand leaves room (kpad <= 512), else 1
-template <int KP, int NBUF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
+// EW  : epilogue warps per TMEM lane quarter, each gating 128 / EW columns of every tile into a list of its own. An
+//       epilogue warp is alone on its scheduler and runs one dependent chain (ncu: one instruction per six cycles), so
+//       a tile costs it 2200 cycles when hardly any row beats the thresholds and two to three times that while the
+//       lists are cold — more than the 3072 cycles of the tile's MMAs. Two warps per quarter halve that: for work items
+//       that are short (small shards) or few (a few hundred queries), where cold lists are the rule.
+template <int KP, int NBUF, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(96 + 128 * EW, 1)
     tensor_filter2_kernel(const __grid_constant__ CUtensorMap tmap_b, FilterArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sb = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int ET = 128;                                                  // epilogue threads per CTA
+  constexpr int ET = 128 * EW;                                             // epilogue threads per CTA
+  constexpr int TF2_STAGES = filter2_stages(KP, EW);
+  constexpr int CW = TF2_BN / EW;                                          // columns of a tile per epilogue warp
   uint32_t* s_crow = reinterpret_cast<uint32_t*>(sb + TF2_STAGES * TF2_STAGE_BYTES);
   float* s_qs = reinterpret_cast<float*>(s_crow + ET * KP);                // [16][ET] queued scores
   uint32_t* s_qc = reinterpret_cast<uint32_t*>(s_qs + 16 * ET);            // [16][ET] queued columns
-  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);                 // [4 warps][2 buffers][128]
+  float* s_aux = reinterpret_cast<float*>(s_qc + 16 * ET);                 // [4 EW warps][2 buffers][CW]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + 4 * 2 * TF2_BN);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = full + TF2_STAGES;         // [STAGES]
   uint64_t* acc_full = empty + TF2_STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
   uint64_t* a_ready = acc_empty + 2;           // [1]
-  uint2* s_hb = reinterpret_cast<uint2*>(a_ready + 1);            // [128] (item, bound) per query row, written by the bound helper (warp 6)
+  uint2* s_hb = reinterpret_cast<uint2*>(a_ready + 1);            // [128] (item, bound) per query row, written by the bound helper (the last warp)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_hb + 128);
   uint32_t* s_cur_item = s_tmem + 1;
 
@@ -760,9 +768,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, 8);             // 4 epilogue warps of each CTA
+      mbar_init(acc_empty + i, 8 * EW);        // the epilogue warps of both CTAs
     }
-    mbar_init(a_ready, 8);
+    mbar_init(a_ready, 8 * EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns of both SMs of the pair
@@ -850,7 +858,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2 + 4 * EW) {
     // ===== bound helper (see publish_two_best): the 128 queries of THIS CTA =====
     if (a.pub) {
       pdl_wait();   // the table is initialised by prep_queries
@@ -860,13 +868,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
     // ===== epilogue warps: thread <-> query (TMEM lane of this CTA) =====
     const uint32_t quarter = warp & 3;
     const uint32_t qrow = quarter * 32 + lane;
+    const uint32_t slice = (warp - 2) >> 2;    // which CW columns of a tile this warp gates
     const uint32_t lane_addr = (quarter * 32) << 16;
     const float INF = __int_as_float(0x7f800000);
     pdl_wait();   // bf16 queries and hints come from prep_queries (chained launch, common.cuh)
-    uint32_t* my_row = s_crow + qrow;          // slot j at [j*ET]
-    float* my_qs = s_qs + qrow;
-    uint32_t* my_qc = s_qc + qrow;
-    float* my_aux = s_aux + (warp - 2) * 2 * TF2_BN;
+    uint32_t* my_row = s_crow + slice * 128 + qrow;   // slot j at [j*ET]
+    float* my_qs = s_qs + slice * 128 + qrow;
+    uint32_t* my_qc = s_qc + slice * 128 + qrow;
+    float* my_aux = s_aux + (warp - 2) * 2 * CW;
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(acc_empty), 0);
     const uint32_t a_ready_leader = mapa_u32(smem_u32(a_ready), 0);
     uint32_t acc_it = 0;
@@ -882,7 +891,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
       {
         const uint4* src = reinterpret_cast<const uint4*>(a.qb + (size_t)q_global * a.kpad);
         const uint32_t n16 = a.kpad / 8;   // 16-byte groups = 4 TMEM columns each; kpad is a multiple of 128: n16 of 16
-        for (uint32_t i0 = 0; i0 < n16; i0 += 16) {   // 16 independent loads in flight per lane before the first store
+        for (uint32_t i0 = slice * 16; i0 < n16; i0 += 16 * EW) {   // 16 independent loads in flight per lane before the first store; the warps of a quarter share the copy
           uint4 v[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) v[u] = __ldg(src + i0 + u);
@@ -909,14 +918,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
       float theta = hint;
       int imax = 0;
       const bool sharing = a.pub != nullptr;   // (see publish_two_best)
-      float* my_pub = a.pub + ((size_t)chunk * a.nq_stride + q_global) * 2;   // (q_global < nq_stride)
+      float* my_pub = a.pub + ((size_t)(chunk * EW + slice) * a.nq_stride + q_global) * 2;   // (q_global < nq_stride)
       bool dirty = false;                      // the list changed since it was last published
       if (sharing && warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, item);
-      // additive term of the 128 columns of a tile: one float4 per lane, fetched one tile ahead
+      // additive term of this warp's CW columns of a tile: one float4 per lane, fetched one tile ahead
       auto load_aux = [&](uint32_t t) -> float4 {
         float4 r = make_float4(INF, INF, INF, INF);
-        if (t < t1) {
-          const uint32_t c = t * TF2_BN + lane * 4;
+        if (lane < CW / 4 && t < t1) {
+          const uint32_t c = t * TF2_BN + slice * CW + lane * 4;
           if (c + 3 < a.n_rows) {
             r = __ldg(reinterpret_cast<const float4*>(a.aux + c));
           } else {
@@ -929,26 +938,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
       };
       float4 aux_next = load_aux(t0);
       for (uint32_t t = t0; t < t1; ++t, ++acc_it) {
-        float* aux_t = my_aux + (acc_it & 1) * TF2_BN;
-        reinterpret_cast<float4*>(aux_t)[lane] = aux_next;
+        float* aux_t = my_aux + (acc_it & 1) * CW;
+        if (lane < CW / 4) reinterpret_cast<float4*>(aux_t)[lane] = aux_next;
         aux_next = load_aux(t + 1);
         __syncwarp();
         const uint32_t buf = (NBUF == 2) ? (acc_it & 1) : 0;
         const uint32_t use = (NBUF == 2) ? (acc_it >> 1) : acc_it;
         mbar_wait(acc_full + buf, use & 1);
         tc_fence_after();
-        float v[TF2_BN];
+        float v[CW];
 #pragma unroll
-        for (int g = 0; g < TF2_BN / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF2_BN + g * 32, v + g * 32);
+        for (int g = 0; g < CW / 32; ++g) tc_ld32(tmem_acc + lane_addr + buf * TF2_BN + slice * CW + g * 32, v + g * 32);
         tc_wait_ld();
         // the accumulator now lives in registers: hand it back to the MMA warp of the leader before gating
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader + buf * 8);
         const float4* aux4 = reinterpret_cast<const float4*>(aux_t);
-        const uint32_t colw = t * TF2_BN;
+        const uint32_t colw = t * TF2_BN + slice * CW;
 #pragma unroll
-        for (int seg = 0; seg < TF2_BN / 16; ++seg) {
+        for (int seg = 0; seg < CW / 16; ++seg) {
           float4 ax[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) ax[i] = aux4[seg * 4 + i];
@@ -1014,19 +1023,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
           theta = fminf(theta, hint);
         }
       }
-      // ---- chunk result: one candidate list per (query, chunk) ----
+      // ---- chunk result: one candidate list per (query, chunk, column slice) ----
       if (q_global < a.nq) {
-        const size_t base = ((size_t)q_global * a.n_chunks + chunk) * KP;
+        const size_t vchunk = (size_t)chunk * EW + slice;
+        const size_t base = ((size_t)q_global * a.n_chunks * EW + vchunk) * KP;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           a.cand_score[base + j] = sc[j];
           a.cand_row[base + j] = my_row[j * ET];
         }
-        a.chunk_tau[(size_t)q_global * a.n_chunks + chunk] = theta;
+        a.chunk_tau[(size_t)q_global * a.n_chunks * EW + vchunk] = theta;
         if (sharing) publish_two_best<KP>(sc, my_pub);   // the list's final two best, for the lists of later waves
         if (a.hint) {
           const float pub = a.hint_target == 0 ? theta
-                                               : fminf(theta, publish_value<KP>(sc, min(a.n_rows, t1 * (uint32_t)TF2_BN) - t0 * (uint32_t)TF2_BN,
+                                               : fminf(theta, publish_value<KP>(sc, (min(a.n_rows, t1 * (uint32_t)TF2_BN) - t0 * (uint32_t)TF2_BN) / EW,
                                                                                 a.n_rows, a.hint_target));
           if (pub < INF) atomicMin(a.hint + q_global, f32_ord(pub));
         }
@@ -1044,39 +1054,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(224, 1)
   }
 }
 
-template <int KP>
+template <int KP, int EW>
 static size_t filter2_smem() {
-  return 1024 + (size_t)TF2_STAGES * TF2_STAGE_BYTES + (size_t)128 * KP * 4 + (size_t)2 * 16 * 128 * 4 + (size_t)4 * 2 * TF2_BN * 4 +
-         (size_t)(2 * TF2_STAGES + 5) * 8 + 128 * 8 + 16;
+  return 1024 + (size_t)filter2_stages(KP, EW) * TF2_STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
+         (size_t)4 * 2 * TF2_BN * 4 + (size_t)(2 * filter2_stages(KP, EW) + 5) * 8 + 128 * 8 + 16;
 }
 
 // CTA pairs that are resident at the same time (not every SM of the part has a free partner in its
 // TPC): the persistent grid is sized to it, so that no pair waits for a second wave.
-template <int KP>
 static int32_t filter2_resident_pairs(int* out) {
-  static int cached = 0;   // per process: one part per box
+  static int cached = 0;   // per process: one part per box (the variants all take a whole SM per CTA)
   if (cached == 0) {
-    SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, 1>), filter2_smem<KP>());
+    SCN_ALLOW_SMEM((tensor_filter2_kernel<16, 1, 1>), (filter2_smem<16, 1>()));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * 74);
     cfg.blockDim = dim3(224);
-    cfg.dynamicSmemBytes = filter2_smem<KP>();
+    cfg.dynamicSmemBytes = filter2_smem<16, 1>();
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tensor_filter2_kernel<KP, 1>, &cfg) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, tensor_filter2_kernel<16, 1, 1>, &cfg) != cudaSuccess || n < 1) {
       cudaGetLastError();
       n = 64;
     }
     cached = n;
-    if (getenv("SCN_DEBUG")) fprintf(stderr, "[scn] tensor_filter2<%d>: %d CTA pairs resident\n", KP, n);
+    if (getenv("SCN_DEBUG")) fprintf(stderr, "[scn] tensor_filter2: %d CTA pairs resident\n", n);
   }
   *out = cached;
   return SCN_OK;
 }
 
-template <int KP, int NBUF>
+template <int KP, int NBUF, int EW>
 static int32_t launch_filter2(const CUtensorMap& tmap_b, const FilterArgs& fa, int pairs, cudaStream_t stream, bool pdl) {
-  SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, NBUF>), filter2_smem<KP>());
-  SCN_CUDA(launch_chained(tensor_filter2_kernel<KP, NBUF>, dim3(2 * pairs), dim3(224), filter2_smem<KP>(), stream, pdl, tmap_b, fa));   // (cluster dims are compiled in)
+  SCN_ALLOW_SMEM((tensor_filter2_kernel<KP, NBUF, EW>), (filter2_smem<KP, EW>()));
+  SCN_CUDA(launch_chained(tensor_filter2_kernel<KP, NBUF, EW>, dim3(2 * pairs), dim3(96 + 128 * EW), filter2_smem<KP, EW>(), stream, pdl, tmap_b,
+                          fa));   // (cluster dims are compiled in)
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -1590,7 +1600,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   // candidates kept per (query, chunk): 16 covers k <= 10 with a 60 % margin, 32 covers k <= 24
   uint32_t kprime = (k <= 10 && s->opt_overfetch <= 16) ? 16u : 32u;
   int resident_pairs = 0;
-  if (pair_kernel) SCN_TRY(kprime == 16 ? filter2_resident_pairs<16>(&resident_pairs) : filter2_resident_pairs<32>(&resident_pairs));
+  if (pair_kernel) SCN_TRY(filter2_resident_pairs(&resident_pairs));
   // (an item of the pair kernel costs about 24 tiles besides its own: measured at C2, 11 chunks 10.9 ms, 24: 11.5, 48: 12.7, 96: 14.0 —
   // every item stages a query block and starts its candidate lists over)
   uint32_t n_chunks = pair_kernel ? pick_chunks((n_qb + 1) / 2, n_tiles, (uint32_t)resident_pairs, 24) : pick_chunks(n_qb, n_tiles, (uint32_t)sms);
@@ -1600,7 +1610,12 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   // epilogue warps per TMEM lane quarter: the gate of a 128x128 tile costs ~1600 issue cycles with
   // one warp per quarter; the MMA of the tile takes 4*kpad cycles
   const bool stream_a = s->kpad > TF_MAX_KPAD;  // query block too wide for TMEM: stream it with the rows
-  const uint32_t ew = (s->kpad >= 640 || dbg_scores || pair_kernel) ? 1u : 2u;
+  // Pair kernel: two warps per quarter. Measured (1 M x 768, cosine; one warp -> two): 256 queries 0.465 -> 0.379 ms, 1024: 1.73 -> 1.22,
+  // 4096: 5.50 -> 4.88, C2 (10 000): filter 11.71 -> 10.99 ms, a 125 k-row shard (8 GPUs): 2.00 -> 1.38 ms.
+  // (Single CTAs on short rows with FOUR warps per quarter were measured too — 1 M x 128, 16 384 queries: 7.78 -> 7.57 ms, small
+  // batches slower, twice the candidates to merge — and dropped: short rows are not bound by the latency of the gate's chain.)
+  const uint32_t pair_ew = s->opt_tensor_pair_ew > 0 ? (uint32_t)std::min<int64_t>(s->opt_tensor_pair_ew, 2) : 2u;
+  const uint32_t ew = pair_kernel ? pair_ew : (s->kpad >= 640 || dbg_scores) ? 1u : 2u;
   const uint32_t n_lists = n_chunks * ew;  // candidate lists per query
   // few lists per query (huge batches) concentrate the global top-k in one list: at wide rows, where
   // the certificate needs a bigger margin, keep 32 per list so that its threshold stays far below
@@ -1629,8 +1644,15 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
 
   // lists of a query exchange bounds while they are built (publish_two_best) when there are at least 16 of them — few
   // queries spread over many row chunks; the deep cut of wide rows (k'' = 64) keeps its own, looser thresholds
+  // Where it pays (measured, 1 M rows): where the gate is what bounds the kernel — short rows (128 elements: 16 queries 0.220 ->
+  // 0.171 ms, 1024 queries 0.99 -> 0.64 ms) — while the lists are cold for most of their life (at most two waves of work items:
+  // 16 384 queries 7.1 -> 7.8 ms) and a warp gates more than a few real queries (one query: 0.125 -> 0.150 ms). Long rows do not
+  // need it: small batches stream the mirror at HBM rate (768 elements, <= 128 queries: +4 %), and the pair kernel with two warps per
+  // quarter keeps up with its MMAs anyway (256 .. 4096 queries: +-1 %).
   const uint32_t lists_pad = (n_lists + 15) / 16 * 16;
-  const bool share = s->opt_tensor_share != 0 && n_lists >= 16 && !stream_a && !dbg_scores;
+  const uint32_t items = (pair_kernel ? (n_qb + 1) / 2 : n_qb) * n_chunks;
+  const bool share = !stream_a && !dbg_scores && n_lists >= 16 &&
+                     (s->opt_tensor_share > 1 || (s->opt_tensor_share == 1 && !pair_kernel && s->kpad <= 256 && items <= 2 * (uint32_t)sms && nq >= 8));
 
   Scratch scratch(stream);
   __nv_bfloat16* d_qb = nullptr;
@@ -1705,8 +1727,13 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   int32_t rc;
   if (pair_kernel) {
     const int pairs = (int)std::min<uint32_t>((uint32_t)resident_pairs, ((n_qb + 1) / 2) * n_chunks);
-    if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 2>(tmap, fa, pairs, stream, pdl);
-    else rc = (kprime == 16) ? launch_filter2<16, 1>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 1>(tmap, fa, pairs, stream, pdl);
+    if (ew == 2) {
+      if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2, 2>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 2, 2>(tmap, fa, pairs, stream, pdl);
+      else rc = (kprime == 16) ? launch_filter2<16, 1, 2>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 1, 2>(tmap, fa, pairs, stream, pdl);
+    } else {
+      if (s->kpad <= 512) rc = (kprime == 16) ? launch_filter2<16, 2, 1>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 2, 1>(tmap, fa, pairs, stream, pdl);
+      else rc = (kprime == 16) ? launch_filter2<16, 1, 1>(tmap, fa, pairs, stream, pdl) : launch_filter2<32, 1, 1>(tmap, fa, pairs, stream, pdl);
+    }
   } else if (stream_a) {
     if (dbg_scores) rc = launch_filter<16, 2, 1, true, true, 128>(tmap, tmap_a, fa, grid, stream, pdl);
     else rc = (kprime == 16) ? launch_filter<16, 2, 1, false, true, 128>(tmap, tmap_a, fa, grid, stream, pdl)

@@ -757,6 +757,8 @@ int32_t scn_set_option(scn_store* s, const char* name, int64_t value) {
     s->opt_tensor_pair = value;
   } else if (n == "tensor_fused") {
     s->opt_tensor_fused = value;
+  } else if (n == "tensor_pair_ew") {
+    s->opt_tensor_pair_ew = value;
   } else if (n == "tensor_share") {
     s->opt_tensor_share = value;
   } else if (n == "pdl") {

@@ -277,10 +277,28 @@ def test_shared_bounds_between_lists_keep_results_and_certificates(metric, n, d,
     s.append(db)
     s.set_option("flat_path", 2)
     o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, nthreads=8)
-    for share in (1, 0):
+    for share in (2, 0):   # 2 = whenever a query has >= 16 lists
         s.set_option("tensor_share", share)
         ids, dist, cnt = s.search_flat(q, k)
         tensor_q, widened, rescanned = s.last_counters()[:3]
         assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt), share
         assert tensor_q == nq and widened <= 0.02 * nq + 1 and rescanned <= widened, (share, widened, rescanned)
+    s.close()
+
+
+@pytest.mark.parametrize("metric", [DistanceMetric.L2, DistanceMetric.COSINE])
+@pytest.mark.parametrize("n,d,nq,k", [(30001, 768, 300, 10), (20000, 600, 256, 24), (50000, 512, 700, 10), (9000, 470, 513, 24)])
+def test_cta_pair_filter_one_and_two_epilogue_warps_per_quarter(metric, n, d, nq, k):
+    # tensor_pair_ew: every TMEM lane quarter of the pair kernel is gated by one warp (128 columns of a tile, one list per
+    # chunk) or by two (64 columns each, two lists per chunk); one and two accumulators, both k' sizes
+    db, q = gaussian(n, d, 41), gaussian(nq, d, 42)
+    s = DeviceStore(d, metric)
+    s.append(db)
+    s.set_option("flat_path", 2)
+    o_ids, o_dist, o_cnt = oracle.flat_search(int(metric), db, q, k, nthreads=8)
+    for ew in (1, 2):
+        s.set_option("tensor_pair_ew", ew)
+        ids, dist, cnt = s.search_flat(q, k)
+        assert np.array_equal(ids, o_ids) and np.array_equal(dist, o_dist) and np.array_equal(cnt, o_cnt), ew
+        assert s.last_counters()[0] == nq
     s.close()
