@@ -1171,7 +1171,7 @@ __device__ __forceinline__ void warp_sort64(uint64_t* a, uint32_t lane) {
 // fall through to the full sort.
 __device__ __forceinline__ uint32_t select_and_sort(uint64_t* keys, uint32_t n, uint32_t n_pad, uint32_t kpp) {
   uint32_t n_sort = n_pad < 64 ? 64u : n_pad;
-  if (n_pad > 512) {
+  if (n_pad > 128) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank, s_cnt, s_total;
     __shared__ uint64_t buf[256];
