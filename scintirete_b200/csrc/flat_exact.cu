@@ -80,14 +80,42 @@ struct ScanParams {
   uint32_t k;
   uint32_t row_base;  // added to the row field of the emitted keys
   uint64_t* partial;  // [gridDim.x][nq][k]
+  unsigned long long one2;  // (1.0f, 1.0f): see pair_step
 };
 
+// One accumulation step for a PAIR of queries on the packed fp32x2 pipe: acc2 += q2 * x2 (or (q2 - x2)^2), every half
+// an IEEE round-to-nearest operation of its own, i.e. bit for bit the scalar __fsub_rn / __fmul_rn / __fadd_rn.
+template <int METRIC>
+__device__ __forceinline__ void pair_step(unsigned long long& acc2, unsigned long long q2, unsigned long long x2, unsigned long long one2) {
+  // The sum is taken as prod * one + acc with `one` = (1.0f, 1.0f) handed in as a KERNEL PARAMETER: one rounding of the exact
+  // value prod + acc, i.e. the add. Spelled add.rn.f32x2, ptxas 12.9 contracts the mul.rn.f32x2 in front of it into ONE FFMA2
+  // — a single rounding of q * x + acc instead of the reference's two — with or without -fmad=false, and also when the one is a
+  // literal or the product is written fma(a, b, -0). A multiplier it cannot see through keeps FMUL2 and FFMA2 apart
+  // (cuobjdump: 128 + 128 per stage). tests/test_gpu_flat.py compares the bits with the oracle's.
+  unsigned long long prod;
+  if (METRIC == M_L2) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(q2), "l"(x2));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(prod) : "l"(d));
+  } else {
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(prod) : "l"(q2), "l"(x2));
+  }
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc2) : "l"(prod), "l"(one2), "l"(acc2));
+}
+
+// The queries of a pass sit in shared memory element-major, s_q[e][QP] with QP = QB rounded up to 2: the values all
+// queries need for element e are adjacent (one or two LDS.128 at an immediate offset), and queries (2p, 2p+1) form the
+// pairs whose sums advance together: per element and pair one FMUL2 and one FADD2 (round 1 spent one FADD per element
+// and QUERY plus half an FMUL2 — 38.7 % + 19.2 % of all issued instructions, and another 22 % on the addresses of
+// query-major rows of run-time length; profiles/r02_ncu_flat_exact_scan_*).
 template <int METRIC, int QB>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanParams p) {
+  constexpr int NP = (QB + 1) / 2;  // query pairs
+  constexpr int QP = 2 * NP;        // floats per element in s_q
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t k = p.k;
-  float* s_q = reinterpret_cast<float*>(smem_raw);                    // [QB][dim_pad]
-  float* s_tile = s_q + (size_t)QB * p.dim_pad;                       // [STAGES][256][PITCH]
+  float* s_q = reinterpret_cast<float*>(smem_raw);                    // [dim_pad][QP]
+  float* s_tile = s_q + (size_t)QP * p.dim_pad;                       // [STAGES][256][PITCH]
   uint64_t* s_queue = reinterpret_cast<uint64_t*>(s_tile + (size_t)SCAN_STAGES * SCAN_THREADS * SCAN_PITCH);  // [QB][256]
   uint64_t* s_list = s_queue + (size_t)QB * SCAN_THREADS;             // [QB][k]
   __shared__ uint64_t s_tau[QB];
@@ -100,19 +128,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
   uint32_t nq_total = p.nq_dev ? min(*p.nq_dev, p.nq) : p.nq;
   const uint32_t n_tiles = (p.n_rows + SCAN_THREADS - 1) / SCAN_THREADS;
   const uint32_t n_chunks = p.dim_pad / SCAN_KC;
+  // this thread's share of every stage copy: 16-byte segment `seg` of rows r0, r0 + 32, ... of the tile
+  const uint32_t r0 = tid >> 3, seg = tid & 7;
 
   for (uint32_t q0 = 0; q0 < nq_total; q0 += QB) {
     const uint32_t nq_here = min((uint32_t)QB, nq_total - q0);
     __syncthreads();
-    // queries -> smem (zero padded), lists -> KEY_NONE
-    for (uint32_t i = tid; i < QB * p.dim_pad; i += SCAN_THREADS) {
-      uint32_t qi = i / p.dim_pad, e = i - qi * p.dim_pad;
+    // queries -> smem (element-major, zero padded), lists -> KEY_NONE
+    for (uint32_t i = tid; i < QP * p.dim_pad; i += SCAN_THREADS) {
+      const uint32_t qi = i / p.dim_pad, e = i - qi * p.dim_pad;   // (consecutive threads read consecutive elements of a query)
       float v = 0.0f;
       if (qi < nq_here && e < p.q_dim) {
         uint32_t src = p.qlist ? p.qlist[q0 + qi] : (q0 + qi);
         v = p.q[(size_t)src * p.q_pitch + e];
       }
-      s_q[i] = v;
+      s_q[(size_t)e * QP + qi] = v;
     }
     for (uint32_t i = tid; i < QB * k; i += SCAN_THREADS) s_list[i] = KEY_NONE;
     if (tid < QB) {
@@ -120,7 +150,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
       s_qcount[tid] = 0;
     }
     __syncthreads();
-    if (METRIC == M_COS && tid < QB) s_qnorm[tid] = exact_norm_thread(s_q + (size_t)tid * p.dim_pad, p.q_dim);
+    if (METRIC == M_COS && tid < QB) {   // ||q|| as the reference sums it (distance.go:58-66)
+      float sum = 0.0f;
+      for (uint32_t e = 0; e < p.q_dim; ++e) {
+        const float v = s_q[(size_t)e * QP + tid];
+        sum = __fadd_rn(sum, __fmul_rn(v, v));
+      }
+      s_qnorm[tid] = __fsqrt_rn(sum);
+    }
     __syncthreads();
 
     // flattened (tile, chunk) pipeline over this block's tiles
@@ -128,44 +165,57 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
     const uint32_t total = my_tiles * n_chunks;
     auto issue = [&](uint32_t it) {
       if (it < total) {
-        uint32_t tile = blockIdx.x + (it / n_chunks) * gridDim.x;
-        uint32_t chunk = it % n_chunks;
-        float* dst = s_tile + (size_t)(it % SCAN_STAGES) * SCAN_THREADS * SCAN_PITCH;
+        const uint32_t tile = blockIdx.x + (it / n_chunks) * gridDim.x;
+        const uint32_t chunk = it % n_chunks;
+        float* dst = s_tile + (size_t)(it % SCAN_STAGES) * SCAN_THREADS * SCAN_PITCH + r0 * SCAN_PITCH + seg * 4;
         // 256 rows x 8 segments of 16 B; consecutive threads take consecutive segments of a row
+        const uint32_t col = chunk * SCAN_KC + seg * 4;
+        const uint32_t row0 = tile * SCAN_THREADS + r0;
+        const bool col_ok = col < p.pitch;
+        const float* src = p.vec + (size_t)row0 * p.pitch + col;
+        const size_t step = (size_t)32 * p.pitch;
 #pragma unroll
-        for (int j = 0; j < (SCAN_THREADS * 8) / SCAN_THREADS; ++j) {
-          uint32_t idx = j * SCAN_THREADS + tid;
-          uint32_t r = idx >> 3, seg = idx & 7;
-          uint32_t row = tile * SCAN_THREADS + r;
-          uint32_t col = chunk * SCAN_KC + seg * 4;
-          bool valid = (row < p.n_rows) && (col < p.pitch);
-          const float* src = p.vec + (size_t)(valid ? row : 0) * p.pitch + (valid ? col : 0);
-          cp_async16(dst + r * SCAN_PITCH + seg * 4, src, valid);
+        for (int j = 0; j < SCAN_THREADS / 32; ++j) {
+          const bool valid = col_ok && (row0 + j * 32 < p.n_rows);
+          cp_async16(dst + j * 32 * SCAN_PITCH, valid ? src + j * step : p.vec, valid);
         }
       }
       cp_async_commit();
     };
     for (int s = 0; s < SCAN_STAGES - 1; ++s) issue(s);
 
-    float acc[QB];
+    unsigned long long acc2[NP];
     for (uint32_t it = 0; it < total; ++it) {
       const uint32_t chunk = it % n_chunks;
       if (chunk == 0) {
 #pragma unroll
-        for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.0f;
+        for (int pr = 0; pr < NP; ++pr) acc2[pr] = 0ull;   // (+0.0, +0.0)
       }
       cp_async_wait<SCAN_STAGES - 2>();
       __syncthreads();                 // stage `it` landed for everyone; stage it-1 is free
       issue(it + SCAN_STAGES - 1);
       const float4* x4 = reinterpret_cast<const float4*>(s_tile + (size_t)(it % SCAN_STAGES) * SCAN_THREADS * SCAN_PITCH +
                                                           tid * SCAN_PITCH);
+      const float* qe = s_q + (size_t)chunk * SCAN_KC * QP;   // the QP query values of element e at qe[e * QP]
 #pragma unroll
       for (int j = 0; j < SCAN_KC / 4; ++j) {
-        float4 x = x4[j];
+        const float4 x = x4[j];
+        const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int qi = 0; qi < QB; ++qi) {
-          float4 qv = *reinterpret_cast<const float4*>(s_q + (size_t)qi * p.dim_pad + chunk * SCAN_KC + j * 4);
-          acc[qi] = acc_step4<METRIC>(acc[qi], qv, x);
+        for (int u = 0; u < 4; ++u) {
+          const unsigned long long x2 = pack_f32x2(xs[u], xs[u]);
+          const float* qv = qe + (j * 4 + u) * QP;
+          if (NP == 1) {
+            const float2 a = *reinterpret_cast<const float2*>(qv);
+            pair_step<METRIC>(acc2[0], pack_f32x2(a.x, a.y), x2, p.one2);
+          } else {
+#pragma unroll
+            for (int h = 0; h < NP / 2; ++h) {
+              const float4 a = *reinterpret_cast<const float4*>(qv + 4 * h);
+              pair_step<METRIC>(acc2[2 * h], pack_f32x2(a.x, a.y), x2, p.one2);
+              pair_step<METRIC>(acc2[2 * h + 1], pack_f32x2(a.z, a.w), x2, p.one2);
+            }
+          }
         }
       }
       if (chunk == n_chunks - 1) {
@@ -177,7 +227,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) flat_exact_scan_kernel(ScanPa
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi) {
           if (qi < (int)nq_here && live) {
-            float d = finish_distance<METRIC>(acc[qi], s_qnorm[qi], xn);
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2[qi >> 1]));
+            float d = finish_distance<METRIC>((qi & 1) ? hi : lo, s_qnorm[qi], xn);
             uint64_t key = make_key(d, row + p.row_base);
             if (key < s_tau[qi]) {
               uint32_t slot = atomicAdd(&s_qcount[qi], 1u);
@@ -244,7 +296,7 @@ __global__ void __launch_bounds__(256) merge_partials_kernel(const uint64_t* __r
 }
 
 static size_t scan_smem_bytes(int qb, uint32_t dim_pad, uint32_t k) {
-  return (size_t)qb * dim_pad * 4 + (size_t)SCAN_STAGES * SCAN_THREADS * SCAN_PITCH * 4 + (size_t)qb * SCAN_THREADS * 8 +
+  return (size_t)((qb + 1) / 2 * 2) * dim_pad * 4 + (size_t)SCAN_STAGES * SCAN_THREADS * SCAN_PITCH * 4 + (size_t)qb * SCAN_THREADS * 8 +
          (size_t)qb * k * 8;
 }
 
@@ -305,6 +357,7 @@ int32_t flat_search_exact(scn_store* s, const float* d_q, const uint32_t* d_qlis
   p.k = k;
   p.row_base = (uint32_t)row_base;
   p.partial = d_partial;
+  p.one2 = 0x3f8000003f800000ull;
   // behind the tensor path this is the last resort and normally has nothing to do: chained launches (see
   // common.cuh) let its start-up overlap the kernels before it
   const bool pdl = s->opt_pdl != 0 && d_nq_dev != nullptr && !(prof && prof->on);
