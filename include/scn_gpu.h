@@ -335,7 +335,7 @@ SCN_API int32_t scn_batcher_stats(scn_batcher* b, uint64_t* out, int32_t n);
  *   "tensor_pair"       1 = CTA-pair filter kernel (tcgen05 cta_group::2) for 448 < dim <= 512 and 576 < dim <= 768 at
  *                       batches of >= 256 queries (default), 0 = the single-CTA kernel everywhere
  *   "tensor_fused"      candidate merge, exact rerank and certificate behind the filter in one launch per batch
- *                       (one block per query): 1 always, 0 never (three grids), -1 auto (batches of <= 2048 queries)
+ *                       (one block per query): 1 always, 0 never (three grids), -1 auto (batches of <= 512 queries)
  *   "tensor_pair_ew"    pair kernel: epilogue warps per TMEM lane quarter (each gates 128 / n columns of a tile into its own
  *                       list): 0 = auto (2), 1, 2
  *   "tensor_share"      1 = the candidate lists of a query exchange bounds while the filter builds them where that pays (rows of

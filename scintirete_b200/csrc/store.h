@@ -83,7 +83,7 @@ struct scn_store {
   int64_t opt_tensor_bn = 0;      // 128 forces 128-row tiles in the tensor filter (0 = auto)
   int64_t opt_tensor_chunks = 0;  // row chunks per query block in the tensor filter; 0 = auto
   int64_t opt_tensor_pair = 1;    // 1 = CTA-pair filter kernel (cta_group::2, M=256 x N=128, queries stationary in TMEM) at kpad 512 / 640 / 768, batches >= 256
-  int64_t opt_tensor_fused = -1;  // merge -> exact rerank -> certificate behind the filter in ONE launch (finish_queries_kernel): 1 always, 0 never, -1 auto (batches of up to 2048 queries)
+  int64_t opt_tensor_fused = -1;  // merge -> exact rerank -> certificate behind the filter in ONE launch (finish_queries_kernel): 1 always, 0 never, -1 auto (batches of up to 512 queries)
   int64_t opt_tensor_pair_ew = 0; // pair kernel: epilogue warps per TMEM lane quarter; 0 = auto (2), 1, 2
   int64_t opt_tensor_share = 1;   // lists of a query exchange bounds while they are built: 1 = where it pays (flat_tensor.cu), 2 = whenever a query has >= 16 lists, 0 = never
   int64_t opt_pdl = 1;            // the short kernels behind the tensor filter are launched chained (programmatic dependent launch, common.cuh)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final round-2 record on one B200: smoke, GPU parity suite, default bench (C2 + C3 + build blocks), reference arm.
+# Final round-2 record on one B200: smoke, GPU parity suite, default bench (C2 + C3 + build blocks), reference arm, ncu.
 O=gpurun_out
 python __graft_entry__.py --smoke > $O/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/r02_smoke.log
 python -m pytest tests -m gpu -q > $O/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/r02_pytest_gpu.log
