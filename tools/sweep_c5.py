@@ -3,8 +3,8 @@ showing the HBM-bound -> tensor-bound crossover of the exact flat search.
 
     python tools/sweep_c5.py [--rows 1000000] [--dims 128,768,1536] [--metric 3] [--out gpurun_out/c5.json]
 
-For every (dim, batch) the device-resident search time is measured with CUDA events (3 warm-ups,
-best-of-5 mean), plus the per-kernel split from the library's own events, and converted into
+For every (dim, batch) the device-resident search time is measured with CUDA events (3 warm-ups, mean over
+30 / 5 / 3 back-to-back calls), the per-kernel split from the library's own events in a second pass, and converted into
   * effective HBM GB/s  = one pass over the rows actually streamed (fp32 rows for the exact scan,
     bf16 mirror for the tensor filter) / time
   * TFLOP/s             = 2*nq*N*D / time
@@ -69,9 +69,9 @@ def main():
             for _ in range(3):
                 run(nq)
             torch.cuda.synchronize()
-            store.set_option("profile", 1)
-            store.last_timings()
-            reps = 5 if nq <= 8192 else 3
+            # the call time WITHOUT the library's per-kernel events (they cost about 2 us per kernel and switch the chained
+            # launches off: rounds 1 and 2a timed with them on and read about 0.06 ms high for small batches)
+            reps = 30 if nq <= 1024 else (5 if nq <= 8192 else 3)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
@@ -79,7 +79,13 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            tim = {k_: v[0] / reps for k_, v in store.last_timings().items()}
+            store.set_option("profile", 1)   # second pass: the per-kernel split
+            store.last_timings()
+            preps = 3
+            for _ in range(preps):
+                run(nq)
+            torch.cuda.synchronize()
+            tim = {k_: v[0] / preps for k_, v in store.last_timings().items()}
             cnt = store.last_counters()
             tensor = cnt[0] > 0
             if tensor:
