@@ -282,8 +282,11 @@ __device__ __forceinline__ void bound_helper_loop(const FilterArgs& a, const uin
   }
 }
 
-template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
-__global__ void __launch_bounds__(96 + 128 * EW, 1)
+// SHARE: the instantiation with the bound helper warp and the publication code (see publish_two_best); without it the
+//        kernel is exactly the one of the first half of round 2 (the extra warp and code cost the gate-bound short rows
+//        about 15 % at big batches, where sharing is off anyway)
+template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN, bool SHARE>
+__global__ void __launch_bounds__(64 + 128 * EW + (SHARE ? 32 : 0), 1)
     tensor_filter_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a, FilterArgs a) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   constexpr int TF_BN = BN;
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(96 + 128 * EW, 1)
         }
       }
     }
-  } else if (warp == 2 + 4 * EW) {
+  } else if (SHARE && warp == 2 + 4 * EW) {
     // ===== bound helper (see publish_two_best) =====
     if (a.pub) {
       pdl_wait();   // the table is initialised by prep_queries
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(96 + 128 * EW, 1)
       }
       float theta = hint;  // min(hint, max of sc[]): the threshold every admitted row must beat
       int imax = 0;        // a slot holding theta
-      const bool sharing = a.pub != nullptr;   // (see publish_two_best)
+      const bool sharing = SHARE && a.pub != nullptr;   // (see publish_two_best)
       float* my_pub = a.pub + ((size_t)(chunk * EW + slice) * a.nq_stride + q_global) * 2;   // (q_global < nq_stride)
       bool dirty = false;                      // the list changed since it was last published
       if (sharing && warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, item);
@@ -599,7 +602,7 @@ __global__ void __launch_bounds__(96 + 128 * EW, 1)
                 }
                 theta = fminf(mv[0], hint);
                 imax = mi[0];
-                dirty = true;
+                if (SHARE) dirty = true;
               }
             }
           }
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(96 + 128 * EW, 1)
       }
       // all MMAs of this item have retired (the last acc_full was waited on), so A may be rewritten
     }
-    if (warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, ITEM_EXIT);   // releases the bound helper
+    if (SHARE && warp == 2 && lane == 0) st_shared_volatile_u32(s_cur_item, ITEM_EXIT);   // releases the bound helper
   }
 
   tc_fence_before();
@@ -1570,13 +1573,14 @@ static uint32_t pick_chunks(uint32_t n_qb, uint32_t n_tiles, uint32_t sms, uint3
   return best_c;
 }
 
-template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN>
+template <int KP, int NBUF, int EW, bool DBG, bool ASM, int BN, bool SHARE = false>
 static int32_t launch_filter(const CUtensorMap& tmap_b, const CUtensorMap& tmap_a, const FilterArgs& fa, int grid, cudaStream_t stream, bool pdl) {
   using Cfg = FilterCfg<KP, NBUF, EW, DBG, ASM, BN>;
   size_t smem = 1024 + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES + (size_t)128 * EW * KP * 4 + (size_t)2 * 16 * 128 * EW * 4 +
                 (size_t)8 * BN * 4 + (size_t)(2 * Cfg::STAGES + 5) * 8 + 128 * 8 + 16;
-  SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>), smem);
-  SCN_CUDA(launch_chained(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN>, dim3(grid), dim3(96 + 128 * EW), smem, stream, pdl, tmap_b, tmap_a, fa));
+  SCN_ALLOW_SMEM((tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN, SHARE>), smem);
+  SCN_CUDA(launch_chained(tensor_filter_kernel<KP, NBUF, EW, DBG, ASM, BN, SHARE>, dim3(grid), dim3(64 + 128 * EW + (SHARE ? 32 : 0)), smem, stream, pdl, tmap_b,
+                          tmap_a, fa));
   SCN_LAUNCHED();
   return SCN_OK;
 }
@@ -1652,7 +1656,7 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   // quarter keeps up with its MMAs anyway (256 .. 4096 queries: +-1 %).
   const uint32_t lists_pad = (n_lists + 15) / 16 * 16;
   const uint32_t items = (pair_kernel ? (n_qb + 1) / 2 : n_qb) * n_chunks;
-  const bool share = !stream_a && !dbg_scores && n_lists >= 16 &&
+  const bool share = !stream_a && !dbg_scores && n_lists >= 16 && (pair_kernel || ew == 2) &&
                      (s->opt_tensor_share > 1 || (s->opt_tensor_share == 1 && !pair_kernel && s->kpad <= 256 && items <= 2 * (uint32_t)sms && nq >= 8));
 
   Scratch scratch(stream);
@@ -1748,6 +1752,9 @@ static int32_t flat_search_tensor_batch(scn_store* s, const float* d_q, uint64_t
   } else if (ew == 1) {
     rc = (kprime == 16) ? launch_filter<16, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl)
                         : launch_filter<32, 1, 1, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl);
+  } else if (share) {
+    rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false, 128, true>(tmap, tmap_a, fa, grid, stream, pdl)
+                        : launch_filter<32, 2, 2, false, false, 128, true>(tmap, tmap_a, fa, grid, stream, pdl);
   } else {
     rc = (kprime == 16) ? launch_filter<16, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl)
                         : launch_filter<32, 2, 2, false, false, 128>(tmap, tmap_a, fa, grid, stream, pdl);
