@@ -8,8 +8,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROFILES = os.path.join(ROOT, "profiles")
 
-OURS = ["r01_bench_c2.json", "r01_bench_c3.json", "r01_bench_c1.json", "r01_bench_c2_8gpu.json", "r01_bench_c4_8gpu.json"]
-REFERENCE = ["r01_bench_c2_reference.json", "r01_bench_c3_reference.json"]
+OURS = ["r01_bench_c2.json", "r01_bench_c3.json", "r01_bench_c1.json", "r01_bench_c2_8gpu.json", "r01_bench_c4_8gpu.json",
+        "r02_bench_default.json", "r02_bench_2gpu.json", "r02_bench_4gpu.json", "r02_bench_8gpu.json"]
+REFERENCE = ["r01_bench_c2_reference.json", "r01_bench_c3_reference.json", "r02_bench_reference.json"]
 
 
 def _line(name):
@@ -61,3 +62,32 @@ def test_workload_table_names_the_baseline_configs():
     assert w["c3"][:5] == (1_000_000, 128, 1, 10_000, 10) and w["c3"][5] == "hnsw"     # configs[2]
     assert w["c1"][:5] == (100_000, 128, 1, 1_000, 10) and w["c1"][5] == "hnsw"        # configs[0]
     assert w["c4"][:5] == (10_000_000, 768, 3, 10_000, 10) and w["c4"][5] == "flat"    # configs[3]
+
+
+@pytest.mark.parametrize("name", ["r02_bench_default.json", "r02_bench_2gpu.json", "r02_bench_4gpu.json", "r02_bench_8gpu.json"])
+def test_round2_lines_are_verified_against_the_oracle_and_carry_their_secondary_blocks(name):
+    d = _line(name)
+    v = d["verified"]
+    assert v["identical"] is True and v["identical_pageable_call"] is True and v["queries"] >= 8
+    assert d["e2e"]["pageable"]["value"] > 0
+    r = d["roofline"]
+    assert abs(r["frac_sustained"] - r["achieved"] / 1386.4) < 1e-3 and r["frac_burst"] < r["frac_sustained"]
+    names = [b["workload"].split(":")[0] for b in d["secondary"]]
+    assert names == (["c3", "build"] if d["n_gpus"] == 1 else ["c4"])
+    for b in d["secondary"]:
+        assert b["verified"]["identical"] is True
+        if b["workload"].startswith("c3"):
+            assert b["verified"]["recall_at_k_gpu"] == b["verified"]["recall_at_k_oracle"]
+            assert all(p["identical_to_oracle_sample"] for p in b["ef_sweep"]) and len(b["ef_sweep"]) >= 4
+            assert 0 < b["roofline"]["frac_dram"] < b["roofline"]["frac"]
+
+
+def test_traffic_table_points_at_committed_captures():
+    # roofline.traffic is read from profiles/traffic.json: every entry names the ncu summary it was taken from
+    with open(os.path.join(PROFILES, "traffic.json")) as f:
+        table = json.load(f)
+    assert table
+    for key, entry in table.items():
+        assert entry["bytes"] > 0
+        src = entry["source"].split(" ")[0]
+        assert src.startswith("profiles/") and os.path.exists(os.path.join(ROOT, src)), (key, src)
